@@ -1,0 +1,87 @@
+"""
+ctypes binding of ``libs3b200.so`` (the C-ABI declared in ``include/s3b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C sparsespatialsampling_b200/csrc``.
+There is no CPU fallback: if the shared library is missing or no CUDA device is present, every compute
+call raises.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_int32, c_int64, c_void_p, c_char_p, c_double, POINTER
+
+import torch as pt
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs3b200.so")
+
+S3_F32 = 0
+S3_F64 = 1
+
+_lib = None
+
+
+class S3Error(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); mirrors include/s3b200.h one to one
+_SIGNATURES = {
+    "s3_last_error": (c_char_p, []),
+    "s3_version": (c_int, []),
+    "s3_launch_count": (c_int64, []),
+    "s3_knn_build": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "s3_knn_free": (c_int, [c_void_p]),
+    "s3_knn_query": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "s3_knn_predict": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "s3_knn_tables": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "s3_interp_gather": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                 c_void_p, c_int, c_void_p]),
+}
+
+
+def exported_symbols():
+    """Names of all entry points declared in include/s3b200.h."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load the shared library (no CUDA call is made here)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise S3Error(f"{LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"or `make -C sparsespatialsampling_b200/csrc`. There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().s3_last_error()
+        raise S3Error(f"s3b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def require_cuda():
+    if not pt.cuda.is_available():
+        raise S3Error("s3b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) tensor, or NULL for None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "tensor passed to the C-ABI must be contiguous"
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(pt.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().s3_launch_count())

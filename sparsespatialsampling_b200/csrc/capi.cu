@@ -1,0 +1,31 @@
+// Library-level entry points: error reporting, version, launch accounting.
+#include <atomic>
+#include <stdarg.h>
+#include "common.cuh"
+#include "../../include/s3b200.h"
+
+namespace s3 {
+
+static thread_local char g_error[1024] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace s3
+
+extern "C" {
+
+const char* s3_last_error(void) { return s3::g_error; }
+
+int s3_version(void) { return 100; }
+
+int64_t s3_launch_count(void) { return s3::g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

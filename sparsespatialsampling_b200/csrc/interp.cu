@@ -1,0 +1,194 @@
+// Export-stage interpolation of snapshot rows onto the sampled grid:
+//   out[c, :] = sum_j w[c, j] * data[idx[c, j], :]
+// Replaces interpolate_data (sparseSpatialSampling/export.py:446-468), which materialises
+// data[idx] ([chunk, k, D, T]) and reduces it on the CPU.
+//
+// Layout: data is [N, L] with L = D*T contiguous per source point (the reference's [N, D, T]),
+// out is [Nc, L]. A CTA owns a tile of kCellsPerCta consecutive cells (callers pass cells in
+// Morton order so neighbouring cells share source rows -> L1/L2 hits) times one column chunk
+// of the row. The (idx, w) tile is staged into shared memory with one 1-D TMA bulk copy
+// (cp.async.bulk + mbarrier); every lane then streams 128-bit column vectors of the k source
+// rows (k independent loads in flight per thread) and writes one 128-bit result.
+#include "common.cuh"
+#include "../../include/s3b200.h"
+
+namespace s3 {
+
+constexpr int kInterpThreads = 128;
+constexpr int kCellsPerCta = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+
+template <typename T, int V>
+struct alignas(sizeof(T) * V) Vec {
+    T v[V];
+};
+
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> ld_stream(const T* p) {
+    // read-only path; rows are re-used by neighbouring cells, so let them allocate in L1
+    return *reinterpret_cast<const Vec<T, V>*>(p);
+}
+
+// MODE 0: fp32 FMA accumulate (fast path). MODE 1: fp64, products then sequential adds without
+// contraction -- the reference's (w * data[idx]).sum(dim=1) evaluation order.
+template <typename Tin, typename Tw, typename Tout, int V, int MODE>
+__global__ void __launch_bounds__(kInterpThreads)
+interp_gather_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
+                     const Tw* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
+                     Tout* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* s_idx = reinterpret_cast<int32_t*>(smem_raw);
+    Tw* s_w = reinterpret_cast<Tw*>(smem_raw + ((sizeof(int32_t) * kCellsPerCta * k + 15) / 16) * 16);
+    __shared__ __align__(8) uint64_t bar;
+
+    const int64_t cell0 = (int64_t)blockIdx.y * kCellsPerCta;
+    const int ncell = (int)((n_cells - cell0) < kCellsPerCta ? (n_cells - cell0) : kCellsPerCta);
+    const uint32_t bytes_idx = (uint32_t)(sizeof(int32_t) * ncell * k);
+    const uint32_t bytes_w = (uint32_t)(sizeof(Tw) * ncell * k);
+    const int32_t* g_idx = idx + cell0 * k;
+    const Tw* g_w = w + cell0 * k;
+    const bool bulk = ((bytes_idx | bytes_w) & 15u) == 0 && ((((uintptr_t)g_idx) | ((uintptr_t)g_w)) & 15u) == 0;
+
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, bytes_idx + bytes_w);
+            tma_load_1d(s_idx, g_idx, bytes_idx, &bar);
+            tma_load_1d(s_w, g_w, bytes_w, &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < ncell * k; i += kInterpThreads) {
+            s_idx[i] = g_idx[i];
+            s_w[i] = g_w[i];
+        }
+        __syncthreads();
+    }
+
+    const int64_t col = ((int64_t)blockIdx.x * kInterpThreads + threadIdx.x) * V;
+    if (col >= row_len) return;
+    const Tin* dcol = data + col;
+
+    for (int c = 0; c < ncell; ++c) {
+        const int32_t* ci = s_idx + c * k;
+        const Tw* cw = s_w + c * k;
+        Tw acc[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = (Tw)0;
+        int j = 0;
+        for (; j + 8 <= k; j += 8) {
+            Vec<Tin, V> x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = ld_stream<Tin, V>(dcol + (int64_t)ci[j + u] * row_len);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const Tw wj = cw[j + u];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    if (MODE == 0) acc[e] = fmaf((float)wj, (float)x[u].v[e], (float)acc[e]);
+                    else acc[e] = __dadd_rn((double)acc[e], __dmul_rn((double)wj, (double)x[u].v[e]));
+                }
+            }
+        }
+        for (; j < k; ++j) {
+            Vec<Tin, V> x = ld_stream<Tin, V>(dcol + (int64_t)ci[j] * row_len);
+            const Tw wj = cw[j];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                if (MODE == 0) acc[e] = fmaf((float)wj, (float)x.v[e], (float)acc[e]);
+                else acc[e] = __dadd_rn((double)acc[e], __dmul_rn((double)wj, (double)x.v[e]));
+            }
+        }
+        const int64_t orow = out_row ? (int64_t)out_row[cell0 + c] : (cell0 + c);
+        Vec<Tout, V> o;
+#pragma unroll
+        for (int e = 0; e < V; ++e) o.v[e] = (Tout)acc[e];
+        *reinterpret_cast<Vec<Tout, V>*>(out + orow * row_len + col) = o;
+    }
+}
+
+template <typename Tin, typename Tw, typename Tout, int MODE>
+static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, const void* w, int64_t n_cells, int k,
+                         const int32_t* out_row, void* out, cudaStream_t stream) {
+    if (n_cells == 0 || row_len == 0) return S3_OK;
+    constexpr int VFULL = 16 / sizeof(Tin);
+    const bool vec_ok = (row_len % VFULL == 0) && (((uintptr_t)data) % 16 == 0) &&
+                        (((uintptr_t)out) % (sizeof(Tout) * VFULL) == 0);
+    const size_t smem = ((sizeof(int32_t) * kCellsPerCta * k + 15) / 16) * 16 + sizeof(Tw) * kCellsPerCta * k;
+    const int64_t tiles = ceil_div(n_cells, kCellsPerCta);
+    S3_REQUIRE(tiles <= 65535 * (int64_t)65535, "too many cells");
+    // blockIdx.y is limited to 65535: fold larger tile counts by looping launches
+    const int64_t max_y = 65535;
+    for (int64_t t0 = 0; t0 < tiles; t0 += max_y) {
+        const int64_t ty = (tiles - t0) < max_y ? (tiles - t0) : max_y;
+        const int64_t cell_off = t0 * kCellsPerCta;
+        const int64_t cells_here = (n_cells - cell_off) < ty * kCellsPerCta ? (n_cells - cell_off) : ty * kCellsPerCta;
+        const int32_t* idx_p = idx + cell_off * k;
+        const Tw* w_p = reinterpret_cast<const Tw*>(w) + cell_off * k;
+        const int32_t* orow_p = out_row ? out_row + cell_off : nullptr;
+        Tout* out_p = reinterpret_cast<Tout*>(out) + (out_row ? 0 : cell_off * row_len);
+        if (vec_ok) {
+            dim3 grid((unsigned)ceil_div(row_len, (int64_t)kInterpThreads * VFULL), (unsigned)ty);
+            interp_gather_kernel<Tin, Tw, Tout, VFULL, MODE><<<grid, kInterpThreads, smem, stream>>>(
+                reinterpret_cast<const Tin*>(data), row_len, idx_p, w_p, cells_here, k, orow_p, out_p);
+        } else {
+            dim3 grid((unsigned)ceil_div(row_len, (int64_t)kInterpThreads), (unsigned)ty);
+            interp_gather_kernel<Tin, Tw, Tout, 1, MODE><<<grid, kInterpThreads, smem, stream>>>(
+                reinterpret_cast<const Tin*>(data), row_len, idx_p, w_p, cells_here, k, orow_p, out_p);
+        }
+        S3_LAUNCH_CHECK();
+    }
+    return S3_OK;
+}
+
+}  // namespace s3
+
+using namespace s3;
+
+extern "C" int s3_interp_gather(const void* d_data, int data_dtype, int64_t n_src, int64_t row_len,
+                                const int32_t* d_idx, const void* d_w, int64_t n_cells, int k,
+                                const int32_t* d_out_row, void* d_out, int out_dtype, void* stream) {
+    S3_REQUIRE(d_data && d_idx && d_w && d_out, "s3_interp_gather: NULL argument");
+    S3_REQUIRE(k >= 1 && k <= 64, "s3_interp_gather: k=%d out of range", k);
+    S3_REQUIRE(n_src >= 1 && row_len >= 0 && n_cells >= 0, "s3_interp_gather: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (data_dtype == S3_F32 && out_dtype == S3_F32)
+        return launch_interp<float, float, float, 0>(d_data, row_len, d_idx, d_w, n_cells, k, d_out_row, d_out, st);
+    if (data_dtype == S3_F32 && out_dtype == S3_F64)
+        return launch_interp<float, double, double, 1>(d_data, row_len, d_idx, d_w, n_cells, k, d_out_row, d_out, st);
+    if (data_dtype == S3_F64 && out_dtype == S3_F64)
+        return launch_interp<double, double, double, 1>(d_data, row_len, d_idx, d_w, n_cells, k, d_out_row, d_out, st);
+    s3::set_error("s3_interp_gather: unsupported dtype combination data=%d out=%d", data_dtype, out_dtype);
+    return S3_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,68 @@
+"""
+Device gather + weighted-sum interpolation (host wrapper around ``s3_interp_gather``).
+
+``interpolate_data`` keeps the reference's signature (sparseSpatialSampling/export.py:446-468).
+"""
+import torch as pt
+
+from . import _lib
+
+_DT = {pt.float32: _lib.S3_F32, pt.float64: _lib.S3_F64}
+
+
+def interp_gather(data: pt.Tensor, idx: pt.Tensor, weights: pt.Tensor, out: pt.Tensor = None,
+                  out_row: pt.Tensor = None, out_dtype=None) -> pt.Tensor:
+    """
+    ``out[c] = sum_j weights[c, j] * data[idx[c, j]]`` on the device.
+
+    :param data: CUDA tensor ``[N, ...]`` (fp32 or fp64), contiguous; trailing dims are flattened into one row
+    :param idx: CUDA int32 ``[Nc, k]``
+    :param weights: CUDA ``[Nc, k]``; fp32 for the fp32 fast path, fp64 for fp64 output
+    :param out_row: optional CUDA int32 ``[Nc]``, destination row of each processed cell
+    """
+    _lib.require_cuda()
+    lib = _lib.load()
+    assert data.is_cuda and idx.is_cuda and weights.is_cuda
+    assert idx.dtype == pt.int32 and idx.dim() == 2
+    data = data.contiguous()
+    n_src = data.size(0)
+    row_len = data.numel() // max(n_src, 1)
+    n_cells, k = idx.shape
+    if out_dtype is None:
+        out_dtype = pt.float32 if (data.dtype == pt.float32 and weights.dtype == pt.float32) else pt.float64
+    want_w = pt.float32 if out_dtype == pt.float32 else pt.float64
+    if weights.dtype != want_w:
+        weights = weights.to(want_w)
+    if out is None:
+        out = pt.empty((n_cells,) + tuple(data.shape[1:]), dtype=out_dtype, device=data.device)
+    assert out.is_contiguous() and out.dtype == out_dtype
+    with pt.cuda.device(data.device):
+        _lib.check(lib.s3_interp_gather(_lib.ptr(data), _DT[data.dtype], n_src, row_len, _lib.ptr(idx.contiguous()),
+                                        _lib.ptr(weights.contiguous()), n_cells, k, _lib.ptr(out_row), _lib.ptr(out),
+                                        _DT[out_dtype], _lib.stream_ptr()))
+    return out
+
+
+def interpolate_data(weights: pt.Tensor, idx_weights: pt.Tensor, data: pt.Tensor, chunk_size: int = 100000,
+                     out_dtype=None) -> pt.Tensor:
+    """
+    Drop-in for the reference's ``interpolate_data(weights, idx_weights, data, chunk_size)``.
+
+    Host tensors are moved to the current CUDA device, interpolated there and returned on the device of ``data``.
+    ``chunk_size`` is accepted for signature compatibility; the kernel never materialises ``data[idx]`` so no
+    chunking over cells is needed.
+    """
+    _lib.require_cuda()
+    dev = pt.device("cuda", pt.cuda.current_device())
+    src_device = data.device
+    d = data.to(dev, non_blocking=True)
+    i = idx_weights.to(dev).to(pt.int32)
+    if out_dtype is None:
+        out_dtype = weights.dtype if weights.dtype in (pt.float32, pt.float64) else pt.float64
+        if d.dtype == pt.float64:
+            out_dtype = pt.float64
+    w = weights.to(dev)
+    if d.dtype not in (pt.float32, pt.float64):
+        d = d.to(pt.float64 if out_dtype == pt.float64 else pt.float32)
+    out = interp_gather(d, i, w, out_dtype=out_dtype)
+    return out if src_device.type == "cuda" else out.to(src_device)

@@ -1,0 +1,75 @@
+"""GPU parity: s3_interp_gather against the CPU oracle of interpolate_data (export.py:446-468)."""
+import numpy as np
+import pytest
+import torch as pt
+
+from oracle import s3_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# tolerance stated by BASELINE.json north_star: fp32 relative 1e-5 (relative to the largest gathered magnitude)
+RTOL_F32 = 1e-5
+
+
+def _case(N, Nc, k, D, T, seed):
+    rng = np.random.default_rng(seed)
+    data = rng.standard_normal((N, D, T)).astype(np.float32)
+    idx = rng.integers(0, N, (Nc, k)).astype(np.int32)
+    w = rng.random((Nc, k))
+    w /= w.sum(1, keepdims=True)
+    return data, idx, w
+
+
+@pytest.mark.parametrize("N,Nc,k,D,T", [
+    (5000, 1777, 8, 1, 1000), (5000, 1000, 8, 2, 500), (3000, 515, 26, 3, 64), (2000, 100, 8, 1, 301),
+    (2000, 33, 26, 1, 7), (100, 1, 8, 1, 4), (4000, 2049, 5, 1, 128),
+])
+def test_fp32_path_within_tolerance(cuda, N, Nc, k, D, T):
+    from sparsespatialsampling_b200.interpolate import interp_gather
+    data, idx, w = _case(N, Nc, k, D, T, N + Nc)
+    ref = orc.interpolate(w, idx.astype(np.int64), data)
+    out = interp_gather(pt.from_numpy(data).cuda(), pt.from_numpy(idx).cuda(), pt.from_numpy(w).float().cuda())
+    assert out.dtype == pt.float32 and tuple(out.shape) == (Nc, D, T)
+    scale = np.abs(data[idx]).max(axis=1)                        # max_k |data[idx[c,k]]|
+    err = np.abs(out.cpu().numpy().astype(np.float64) - ref)
+    assert (err <= RTOL_F32 * np.maximum(scale, 1e-30)).all(), err.max()
+
+
+@pytest.mark.parametrize("N,Nc,k,D,T", [(3000, 700, 8, 2, 100), (3000, 300, 26, 1, 33)])
+def test_fp64_path_bit_exact_vs_oracle(cuda, N, Nc, k, D, T):
+    from sparsespatialsampling_b200.interpolate import interp_gather
+    data, idx, w = _case(N, Nc, k, D, T, 3)
+    ref = orc.interpolate(w, idx.astype(np.int64), data)
+    out = interp_gather(pt.from_numpy(data).cuda(), pt.from_numpy(idx).cuda(), pt.from_numpy(w).cuda(),
+                        out_dtype=pt.float64)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    data64 = data.astype(np.float64)
+    out64 = interp_gather(pt.from_numpy(data64).cuda(), pt.from_numpy(idx).cuda(), pt.from_numpy(w).cuda())
+    assert np.array_equal(out64.cpu().numpy(), orc.interpolate(w, idx.astype(np.int64), data64))
+
+
+def test_out_row_permutation_and_linearity(cuda):
+    from sparsespatialsampling_b200.interpolate import interp_gather
+    data, idx, w = _case(4000, 1234, 8, 1, 256, 9)
+    d = pt.from_numpy(data).cuda()
+    i = pt.from_numpy(idx).cuda()
+    wt = pt.from_numpy(w).float().cuda()
+    base = interp_gather(d, i, wt)
+    perm = pt.randperm(1234, device="cuda")
+    out = pt.zeros_like(base)
+    interp_gather(d, i[perm].contiguous(), wt[perm].contiguous(), out=out, out_row=perm.to(pt.int32))
+    assert pt.equal(out, base)
+    # linearity in the data: I(a*x) == a*I(x) for a power of two (exact in fp32)
+    assert pt.equal(interp_gather(d * 4.0, i, wt), base * 4.0)
+    # constant field is reproduced (weights sum to one)
+    ones = pt.ones_like(d)
+    assert pt.allclose(interp_gather(ones, i, wt), pt.ones_like(base), rtol=0, atol=5e-7)
+
+
+def test_reference_signature_interpolate_data(cuda):
+    # interpolate_data(weights, idx_weights, data, chunk_size) with host tensors, fp64 weights -> fp64 result
+    from sparsespatialsampling_b200.interpolate import interpolate_data
+    data, idx, w = _case(2000, 500, 8, 2, 50, 21)
+    out = interpolate_data(pt.from_numpy(w), pt.from_numpy(idx.astype(np.int64)), pt.from_numpy(data), 100)
+    assert out.dtype == pt.float64 and not out.is_cuda
+    assert np.array_equal(out.numpy(), orc.interpolate(w, idx.astype(np.int64), data))
