@@ -56,6 +56,67 @@ int s3_knn_predict(const s3_knn_t* h, const double* d_query, int64_t nq, int k, 
 int s3_knn_tables(const s3_knn_t* h, const double* d_query, int64_t nq, int k, int32_t* d_idx,
                   float* d_w32, double* d_w64, void* stream);
 
+/* ---- refinement engine (device side of SamplingTree, sparseSpatialSampling/s_cube.py) -------------
+ * Cell state: structure of arrays indexed by the reference's cell index (creation order):
+ *   d_center fp64 [cap, dim], d_level int32 [cap], d_lattice int32 [cap, dim] (integer position of the
+ *   cell at its own level), d_gain fp64 [cap], d_metric fp64 [cap], d_flags uint8 [cap]
+ *   (bit 0 = leaf, bit 1 = invalid / removed by a geometry).                                         */
+
+/* children of `d_parents[i]` get indices first_child + i*2^dim + c, c in CH order
+ * (s_cube.py:29,188-194); centre = fl(parent + dir * 0.25*width/2^level) (s_cube.py:399-445,865-902);
+ * parents lose, children get the leaf flag (_update_leaf_cells, s_cube.py:243-251)                 */
+int s3_cells_refine(double* d_center, int32_t* d_level, int32_t* d_lattice, uint8_t* d_flags,
+                    const int64_t* d_parents, int64_t n_parents, int64_t first_child, int dim,
+                    double width, void* stream);
+
+/* SamplingTree._update_gain (s_cube.py:207-241) + numba _update_gain (s_cube.py:1840-1859):
+ * KNN/IDW metric at the cell centre and at the 2^dim would-be child centres, sum|m0-mj|, gain.
+ * Cells: d_cells[i] (int64 [n]) if non-NULL, else first + i. sdm_order: association of the 8-term
+ * sum in 3-D (0 sequential, 1 = torch's 4-lane order); 2-D is always sequential.                    */
+int s3_cells_gain(const s3_knn_t* knn, const double* d_center, const int32_t* d_level,
+                  const int64_t* d_cells, int64_t first, int64_t n, int k, double width, double gain0,
+                  int sdm_order, double* d_metric, double* d_gain, void* stream);
+
+/* _remove_invalid_cells / _check_cell_validity / GeometryObject.check_cell / _apply_mask
+ * (s_cube.py:669-732,1816-1837; geometry/geometry_base.py:40-76; the shape files under geometry/).
+ * Geometry tables: d_geom_hdr int32 [n_geoms,4] = {type, keep_inside, param offset, n_extra},
+ * d_geom_par fp64 flat parameters (layout per type: the classes in sparsespatialsampling_b200/geometry).
+ * only_geom >= 0 restricts the test to one geometry; refine_mode = the reference's refine_geometry;
+ * apply != 0 additionally marks invalid cells (flags = invalid, gain = 0; s_cube.py:721-731).
+ * d_invalid uint8 [n]: 1 where check_cell() returned True for some geometry.                        */
+int s3_cells_mask(const double* d_center, const int32_t* d_level, const int64_t* d_cells, int64_t first,
+                  int64_t n, int dim, double width, const int32_t* d_geom_hdr, const double* d_geom_par,
+                  int n_geoms, int only_geom, int refine_mode, int apply, uint8_t* d_invalid,
+                  uint8_t* d_flags, double* d_gain, void* stream);
+
+/* GeometryObject.check_cell on explicit node sets: d_nodes fp64 [n, n_nodes, dim] -> d_invalid uint8 [n]
+ * (geometry/geometry_base.py:150-163 and the per-shape check_cell methods)                           */
+int s3_nodes_mask(const double* d_nodes, int64_t n, int n_nodes, int dim, const int32_t* d_geom_hdr,
+                  const double* d_geom_par, int n_geoms, int only_geom, int refine_mode,
+                  uint8_t* d_invalid, void* stream);
+/* per-point inside mask of geometry `geom` (the reference's _mask_* / check_triangle / check_tetrahedron) */
+int s3_points_inside(const double* d_points, int64_t n, int dim, const int32_t* d_geom_hdr,
+                     const double* d_geom_par, int geom, uint8_t* d_inside, void* stream);
+
+/* heapq.nlargest(k, leaf, key=(gain, -idx)) (s_cube.py:601-602): radix select + stable radix sort.
+ * d_out int64 [k], ordered by (gain descending, index ascending). Requires k <= number of leaves.   */
+int s3_select_topk(const double* d_gain, const uint8_t* d_flags, int64_t n_cells, int64_t k,
+                   int64_t* d_out, void* stream);
+
+/* final grid assembly (_resort_nodes_and_indices_of_grid, s_cube.py:734-772): corners of the leaf cells
+ * `d_leaves` (int64 [n_leaves], output order) de-duplicated on the finest lattice.
+ * d_faces int32 [n_leaves, 2^dim] (corner order CH), d_vertices fp64 [>= n_leaves*2^dim, dim] (first
+ * *n_vertices rows are valid). Synchronises `stream`.                                               */
+int s3_build_nodes(const int64_t* d_leaves, int64_t n_leaves, const double* d_center,
+                   const int32_t* d_level, const int32_t* d_lattice, int dim, int max_level, double width,
+                   int32_t* d_faces, double* d_vertices, int64_t* n_vertices, void* stream);
+
+/* sum of metric^2 over the leaves (_compute_captured_metric, s_cube.py:317-336) and of a plain
+ * vector (the target norm, s_cube.py:205); d_out fp64 [1]; deterministic reduction tree             */
+int s3_leaf_sumsq(const double* d_metric, const uint8_t* d_flags, int64_t n_cells, double* d_out,
+                  void* stream);
+int s3_sumsq(const double* d_x, int64_t n, double* d_out, void* stream);
+
 /* ---- export-stage interpolation ---------------------------------------------------------------
  * replaces interpolate_data (sparseSpatialSampling/export.py:446-468):
  *   out[c, :] = sum_j w[c, j] * data[idx[c, j], :],  data [n_src, row_len], out [n_cells, row_len]

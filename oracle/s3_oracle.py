@@ -155,3 +155,285 @@ def interpolate(weights: np.ndarray, idx: np.ndarray, data: np.ndarray, chunk_si
             acc = acc + prod[:, j]
         out[s:e] = acc
     return out
+
+
+# ---------------------------------------------------------------------------------- geometry masks
+G_CUBE, G_SPHERE, G_CYLINDER, G_TRIANGLE, G_PRISM, G_TETRA, G_PYRAMID, G_STL, G_POLY2D = range(9)
+
+
+def _flat(t):
+    return [float(v) for v in np.asarray(t, dtype=np.float64).reshape(-1)]
+
+
+def geometry_params(g):
+    """
+    (type id, fp64 parameters, n_extra) of a geometry object, read from the attributes the reference classes
+    define (sparseSpatialSampling/geometry/*.py) -- works on reference objects and on the product's mirrors alike.
+    """
+    t = g.type
+    if t == "cube":
+        return G_CUBE, _flat(g._lower_bound) + _flat(g._upper_bound), 0
+    if t == "sphere":
+        return G_SPHERE, _flat(g._position) + [float(g._radius)], 0
+    if t == "cylinder":
+        cone = not isinstance(g._radius, (int, float))
+        r0, r1 = (g._radius[0], g._radius[1]) if cone else (g._radius, g._radius)
+        return G_CYLINDER, (_flat(g._position[0]) + _flat(g._axis) + [float(g._norm), float(r0), float(r1),
+                                                                     1.0 if cone else 0.0]), 0
+    if t == "triangle":
+        return G_TRIANGLE, _flat(np.stack([np.asarray(p, dtype=np.float64) for p in g._points])), 0
+    if t == "prism":
+        dims = [int(v) for v in g._dim]
+        tri = np.asarray(g._positions[0], dtype=np.float64)[:, dims]
+        return G_PRISM, (_flat(g._positions[0][0]) + _flat(g._axis) + [float(g._norm), float(dims[0]), float(dims[1])]
+                         + _flat(tri)), 0
+    if t == "tetrahedron":
+        return G_TETRA, _flat(g._positions) + _flat(np.asarray(g._normals, dtype=np.float64).T), 0
+    if t == "pyramid":
+        par = []
+        for tet in g._tets:
+            par += geometry_params(tet)[1]
+        return G_PYRAMID, par, 0
+    if t == "STL":
+        tri = np.asarray(g._triangles, dtype=np.float64).reshape(-1, 9)
+        return G_STL, _flat(g._lower_bound) + _flat(g._upper_bound) + [float(g._tolerance)] + _flat(tri), tri.shape[0]
+    if t == "coord_2D":
+        v = np.asarray(g._vertices, dtype=np.float64).reshape(-1, 2)
+        return G_POLY2D, _flat(g._lower_bound) + _flat(g._upper_bound) + _flat(v), v.shape[0]
+    raise ValueError(f"unknown geometry type {t}")
+
+
+def points_inside(g, points: np.ndarray) -> np.ndarray:
+    """Per-point inside mask of geometry ``g`` (the reference's mask_box / mask_sphere / _mask_* functions)."""
+    lib = _load_c()
+    if not hasattr(lib, "_s3o_pi_ready"):
+        lib.s3o_points_inside.restype = None
+        lib.s3o_points_inside.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_int, ctypes.c_void_p]
+        lib._s3o_pi_ready = True
+    type_id, par, n_extra = geometry_params(g)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    out = np.empty(pts.shape[0], dtype=np.uint8)
+    lib.s3o_points_inside(type_id, par.ctypes.data, n_extra, pts.ctypes.data, pts.shape[0], pts.shape[1],
+                          out.ctypes.data)
+    return out.astype(bool)
+
+
+def apply_mask(mask: np.ndarray, keep_inside: bool, refine_geometry: bool) -> bool:
+    """GeometryObject._apply_mask (geometry_base.py:40-76)."""
+    if not refine_geometry:
+        return bool(mask.all()) if not keep_inside else bool(not mask.any())
+    return bool(mask.any()) if not keep_inside else bool(not mask.all())
+
+
+def check_cell(g, nodes: np.ndarray, refine_geometry: bool = False) -> bool:
+    return apply_mask(points_inside(g, nodes), g.keep_inside, refine_geometry)
+
+
+# ------------------------------------------------------------------------------ refinement loop
+DIRS_2D = np.array([[-1, -1], [-1, 1], [1, 1], [1, -1]], dtype=np.float64)
+DIRS_3D = np.array([[-1, -1, 1], [-1, 1, 1], [1, 1, 1], [1, -1, 1], [-1, -1, -1], [-1, 1, -1], [1, 1, -1], [1, -1, -1]],
+                   dtype=np.float64)
+
+
+def gain_formula(level, n_dims, width, gain0, sdm):
+    """numba fastmath _update_gain (s_cube.py:1840-1859), probed form: (((1/2^d) * c^d) * sdm) / gain0."""
+    c = width / (2 ** level)
+    q = c * c if n_dims == 2 else (c * c) * c
+    return (((1 / (2 ** n_dims)) * q) * sdm) / gain0
+
+
+def sum_delta_metric(m: np.ndarray, order: int) -> np.ndarray:
+    """(|m0 - mj|).sum(dim=1) with torch's association order (s_cube.py:229); order 1 = four-lane (3-D, probed)."""
+    a = np.abs(m[:, [0]] - m[:, 1:])
+    if a.shape[1] == 8 and order == 1:
+        return (((a[:, 0] + a[:, 4]) + (a[:, 1] + a[:, 5])) + (a[:, 2] + a[:, 6])) + (a[:, 3] + a[:, 7])
+    s = a[:, 0].copy()
+    for j in range(1, a.shape[1]):
+        s = s + a[:, j]
+    return s
+
+
+class OracleTree:
+    """
+    CPU restatement of SamplingTree (s_cube.py:86-902, 1538-1584) on flat Python lists; control flow and the set
+    operations that define the cell numbering follow the reference line by line.
+    ``max_delta_level`` is not restated.
+    """
+
+    def __init__(self, vertices, target, geometries, n_cells=None, uniform_level=5, min_metric=0.75,
+                 n_cells_iter_start=None, n_cells_iter_end=None, relTol=1e-3, reach_at_least=0.75, pre_select=False,
+                 sdm_order=1):
+        self.X = np.ascontiguousarray(vertices, dtype=np.float64)
+        self.y = np.ascontiguousarray(target, dtype=np.float64)
+        self.geometries = geometries
+        self.d = self.X.shape[1]
+        self.k = 8 if self.d == 2 else 26
+        self.nch = 2 ** self.d
+        self.dirs = DIRS_2D if self.d == 2 else DIRS_3D
+        self.n_cells_max, self.min_metric, self.min_level = n_cells, min_metric, uniform_level
+        self.cpi_start = int(0.001 * self.X.shape[0]) if n_cells_iter_start is None else n_cells_iter_start
+        if self.cpi_start <= 0:
+            self.cpi_start = 1
+        self.cpi_end = self.cpi_start if n_cells_iter_end is None else n_cells_iter_end
+        self.cpi, self.cpi_last = self.cpi_start, 1e9
+        self.relTol, self.reach_at_least, self.pre_select, self.sdm_order = relTol, reach_at_least, pre_select, sdm_order
+        self.metric_log, self.n_cells_log = [], []
+        self.center, self.level, self.gain, self.metric, self.invalid = [], [], [], [], []
+        self.leaf = set()
+        self.iterations = 0
+        # root (s_cube.py:338-397)
+        mid = None
+        for g in geometries:
+            if g.keep_inside:
+                self.width = float(g.main_width)
+                mid = np.asarray(g.center, dtype=np.float64)
+        c = np.repeat(mid[None, :], self.nch + 1, axis=0)
+        c[1:] += self.dirs * 0.25 * self.width
+        m = knn_predict(self.X, self.y, c, self.k)
+        g0 = pow(self.width / 2, self.d) * sum([abs(m[0] - m[i]) for i in range(1, len(m))])
+        if abs(g0 - 0) < 1e-6:
+            g0 = 1.0
+        self.gain0 = float(g0)
+        self.center.append(c[0].copy()); self.level.append(0); self.gain.append(self.gain0)
+        self.metric.append(float(m[0])); self.invalid.append(False)
+        self.leaf.add(0)
+        self.target_norm = float(np.linalg.norm(self.y))
+
+    def _refine_cells(self, to_refine):
+        parents = list(to_refine)
+        first = len(self.center)
+        all_parents, all_children = set(), set()
+        new_index = first
+        for i in parents:
+            off = self.dirs * 0.25 * self.width / (2 ** self.level[i])
+            ch = self.center[i][None, :] + off
+            for j in range(self.nch):
+                self.center.append(ch[j]); self.level.append(self.level[i] + 1)
+                self.gain.append(0.0); self.metric.append(0.0); self.invalid.append(False)
+            all_children.update(list(range(new_index, new_index + self.nch)))
+            all_parents.add(i)
+            new_index += self.nch
+        self.leaf -= all_parents
+        self.leaf.update(all_children)
+        new = list(range(first, new_index))
+        self._update_gain(new)
+        return new
+
+    def _update_gain(self, cells):
+        if not cells:
+            return
+        n = len(cells)
+        q = np.empty((n, self.nch + 1, self.d))
+        for t, i in enumerate(cells):
+            q[t, 0] = self.center[i]
+            q[t, 1:] = self.center[i][None, :] + self.dirs * 0.25 * self.width / (2 ** self.level[i])
+        m = knn_predict(self.X, self.y, q.reshape(-1, self.d), self.k).reshape(n, self.nch + 1)
+        sdm = sum_delta_metric(m, self.sdm_order)
+        for t, i in enumerate(cells):
+            self.gain[i] = gain_formula(self.level[i], self.d, self.width, self.gain0, float(sdm[t]))
+            self.metric[i] = float(m[t, 0])
+
+    def _nodes(self, i):
+        return self.center[i][None, :] + self.dirs * 0.5 * self.width / (2 ** self.level[i])
+
+    def _remove_invalid_cells(self, refined, refine_geometry=False, geometry_no=None):
+        if self.pre_select:
+            return None
+        geoms = self.geometries if geometry_no is None else [self.geometries[geometry_no]]
+        result = []
+        for c in refined:
+            nodes = self._nodes(c)
+            hit = None
+            for g in geoms:
+                if check_cell(g, nodes, refine_geometry):
+                    hit = c
+                    break
+            result.append(hit)
+        idx = set(filter(None, result))
+        if idx == set():
+            return None
+        if refine_geometry:
+            return idx
+        for c in idx:
+            self.invalid[c] = True
+            self.gain[c] = 0
+        self.leaf -= idx
+        return None
+
+    def _captured(self):
+        cur = np.array([self.metric[c] for c in self.leaf])
+        self.metric_log.append(float(np.linalg.norm(cur) / self.target_norm))
+
+    def _continue(self):
+        if self.n_cells_max is None:
+            if len(self.metric_log) > 1 and self.metric_log[-1] / self.min_metric >= self.reach_at_least:
+                return self.metric_log[-1] < self.min_metric and abs(self.metric_log[-1] - self.metric_log[-2]) > self.relTol
+        else:
+            if len(self.leaf) / self.n_cells_max >= self.reach_at_least:
+                rel = abs(self.cpi / self.n_cells_max - self.cpi_last / self.n_cells_max)
+                return len(self.leaf) < self.n_cells_max and rel > self.relTol
+        return True
+
+    def _update_cpi(self):
+        if self.n_cells_max is None:
+            dx, cx = self.min_metric - self.metric_log[0], self.metric_log[-1]
+        else:
+            dx, cx = self.n_cells_max - self.n_after_uniform, len(self.center)
+        new = self.cpi_start - ((self.cpi_start - self.cpi_end) / dx) * cx
+        self.cpi_last = self.cpi
+        self.cpi = int(new) if new > 1 else 1
+
+    def refine(self):
+        import heapq
+        for _ in range(self.min_level):
+            new = self._refine_cells(self.leaf)
+            self._remove_invalid_cells({c for c in new})
+        self.n_after_uniform = len(self.leaf)
+        if self.n_cells_max is None:
+            self._captured()
+        self.n_cells_log.append(len(self.leaf))
+        self.selected_log = []
+        while self._continue():
+            if len(self.metric_log) >= 2:
+                self._update_cpi()
+            srt = heapq.nlargest(min(self.cpi, len(self.center)), self.leaf, key=lambda i: (self.gain[i], -i))
+            self.selected_log.append(list(srt))
+            to_refine = set()
+            for i in srt:
+                to_refine.add(i)
+            self._remove_invalid_cells({c for c in self._refine_cells(to_refine)})
+            if self.n_cells_max is None:
+                self._captured()
+            self.iterations += 1
+            self.n_cells_log.append(len(self.leaf))
+        if self.n_cells_max is not None:
+            self._captured()
+        # geometry refinement (s_cube.py:774-863)
+        for gi, g in enumerate(self.geometries):
+            if not g.refine:
+                continue
+            found = self._remove_invalid_cells(self.leaf, True, gi)
+            if found is None:
+                break
+            cells = set(found)
+            lo = min(self.level[c] for c in cells)
+            hi = max(self.level[c] for c in cells) if g.min_refinement_level is None else g.min_refinement_level
+            while hi > lo:
+                to_refine = set()
+                for i in cells:
+                    if self.level[i] < hi:
+                        to_refine.add(i)
+                idx_new = {c for c in self._refine_cells(to_refine)}
+                self._remove_invalid_cells(idx_new, geometry_no=gi)
+                found = self._remove_invalid_cells({i for i in idx_new if not self.invalid[i]}, True, gi)
+                if found is None:
+                    break
+                cells = set(found)
+                lo += 1
+        order = list(self.leaf)
+        self.all_centers = np.stack([self.center[c] for c in order])
+        self.all_levels = np.array([self.level[c] for c in order], dtype=np.int64)[:, None]
+        self.leaf_order = order
+        return self

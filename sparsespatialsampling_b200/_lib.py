@@ -34,6 +34,20 @@ _SIGNATURES = {
     "s3_knn_query": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "s3_knn_predict": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "s3_knn_tables": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "s3_cells_refine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_double,
+                                c_void_p]),
+    "s3_cells_gain": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_double, c_double, c_int,
+                              c_void_p, c_void_p, c_void_p]),
+    "s3_cells_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p, c_int,
+                              c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "s3_nodes_mask": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                              c_void_p]),
+    "s3_points_inside": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "s3_select_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "s3_build_nodes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p,
+                               POINTER(c_int64), c_void_p]),
+    "s3_leaf_sumsq": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "s3_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "s3_interp_gather": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                  c_void_p, c_int, c_void_p]),
 }

@@ -17,7 +17,7 @@ constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;
 constexpr int kSortWarps = kSortThreads / 32;
 
-__global__ void __launch_bounds__(kSortThreads)
+static __global__ void __launch_bounds__(kSortThreads)
 radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist,
                   int nblocks) {
     __shared__ uint32_t sh[256];
@@ -39,7 +39,7 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, uint3
 }
 
 // Exclusive scan of `count` u32 entries, single block (count = 256 * nblocks is small).
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ data, int64_t count) {
+static __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ data, int64_t count) {
     __shared__ uint32_t partial[1024];
     const int t = threadIdx.x;
     const int64_t chunk = (count + 1023) / 1024;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(kSortThreads)
+static __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                      const uint32_t* __restrict__ offsets, int nblocks) {

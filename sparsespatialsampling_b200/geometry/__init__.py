@@ -1,0 +1,6 @@
+from .base import GeometryObject
+from .analytic import (CubeGeometry, SphereGeometry, CylinderGeometry3D, TriangleGeometry, PrismGeometry3D,
+                       TetrahedronGeometry3D, PyramidGeometry3D)
+
+__all__ = ["GeometryObject", "CubeGeometry", "SphereGeometry", "CylinderGeometry3D", "TriangleGeometry",
+           "PrismGeometry3D", "TetrahedronGeometry3D", "PyramidGeometry3D"]
