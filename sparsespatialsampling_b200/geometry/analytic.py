@@ -173,7 +173,8 @@ class TriangleGeometry(GeometryObject):
         self._type = "triangle"
         assert isinstance(points, (list, tuple, pt.Tensor)), (f"Expected the points to be a list or pt.Tensor, but "
                                                               f"found type {type(points)} instead.")
-        self._points = [pt.as_tensor(p).type(F64) for p in points]
+        # python lists are read as fp64 (the reference runs with torch's default dtype set to float64)
+        self._points = [p.type(F64) if isinstance(p, pt.Tensor) else pt.tensor(p, dtype=F64) for p in points]
         self._check_geometry()
         stacked = pt.stack(self._points, dim=0)
         # triangle_geometry.py:180-199

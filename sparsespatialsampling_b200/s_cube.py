@@ -112,6 +112,7 @@ class SamplingTree(object):
         self.face_ids = None
         self._metric = []
         self._n_cells_log = []
+        self._selected_log = None       # set to [] before refine() to record the selected cells per iteration
         self._n_cells_orig = target.size(0)
         self.data_final_mesh = {}
         self._times = _initialize_time_dict()
@@ -404,6 +405,8 @@ class SamplingTree(object):
                 self._compute_n_cells_per_iter()
 
             _leaf_cells_sorted = self._select(min(self._cells_per_iter, self._n_cells))
+            if self._selected_log is not None:
+                self._selected_log.append(list(_leaf_cells_sorted))
             to_refine = set()
             for i in _leaf_cells_sorted:
                 to_refine.add(i)
