@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the S^3 hot path on B200.
+
+Metric (BASELINE.json): snapshot-points interpolated per second (export-stage interpolation of every original
+snapshot onto the sampled grid), with the grid-generation seconds and the HBM roofline fraction beside it.
+
+One "step" = one pass of the export interpolation over one batch of synthetic input: the scalar field p (D=1) and the
+vector field U (D=2) of the C2 configuration (cylinder2D_Re100-sized: ~100k points, 1000 snapshots) interpolated onto
+the grid S^3 generated for that cloud. Per GPU the batch is fixed (weak scaling: rank r owns its own window of 1000
+snapshots); the sampled grid and the KNN tables are computed on rank 0 and broadcast over NCCL once.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl s3b200|reference]
+  torchrun ... bench.py --gpus N ...                     (one rank per GPU)
+
+`--impl reference` times the reference's CPU evaluation strategy (oracle port, torch CPU operators, all host threads)
+on a bounded snapshot sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch as pt
+
+import synth
+
+METRIC = "snapshot_points_interpolated_per_s"
+UNIT = "snapshot-points/s"
+WORKLOAD = "C2: cylinder2D_Re100-sized synthetic field (~100k pts, 1000 snapshots, p/U export)"
+N_POINTS, N_SNAP = synth.CONFIGS["C2"][0], synth.CONFIGS["C2"][1]
+GRID_KW = dict(uniform_level=5, min_metric=0.75)
+CPU_SAMPLE_SNAPSHOTS = 32
+
+
+def geometries(geo):
+    return [geo.CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"]),
+            geo.SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"], refine=True)]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(n_unique, n_cells, k, comps, t):
+    """unique source rows read once + result written once + the (idx, w) tables."""
+    return n_unique * comps * t * 4 + n_cells * comps * t * 4 + n_cells * k * 8
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import s3_oracle as orc
+
+    class _G:      # tiny geometry shells with the attributes the oracle reads
+        pass
+    dom, cyl = _G(), _G()
+    dom.type, dom.keep_inside, dom.refine, dom.min_refinement_level = "cube", True, False, None
+    dom._lower_bound, dom._upper_bound = synth.CYL2D["lower"], synth.CYL2D["upper"]
+    dom.main_width, dom.center = 2.2, np.array([1.1, 0.205])
+    cyl.type, cyl.keep_inside, cyl.refine, cyl.min_refinement_level = "sphere", False, True, None
+    cyl._position, cyl._radius = synth.CYL2D["pos"], synth.CYL2D["radius"]
+    cyl.main_width, cyl.center = 0.05, np.array(synth.CYL2D["pos"])
+
+    x = synth.cylinder2d_cloud(N_POINTS, seed=0)
+    m = synth.wake_metric(x)
+    t0 = time.time()
+    tree = orc.OracleTree(x.numpy(), m.numpy(), [dom, cyl], **GRID_KW, sdm_order=1).refine()
+    t_grid = time.time() - t0
+    nc = tree.all_centers.shape[0]
+    from sklearn.neighbors import NearestNeighbors
+    t0 = time.time()
+    dist, idx = NearestNeighbors(n_neighbors=8, n_jobs=os.cpu_count()).fit(x.numpy()).kneighbors(tree.all_centers)
+    w = pt.from_numpy(orc.export_weights(dist))
+    t_knn = time.time() - t0
+    idx = pt.from_numpy(idx)
+    ts = CPU_SAMPLE_SNAPSHOTS
+    p = synth.wake_field(x, 0, ts, N_SNAP, 1)
+    u = synth.wake_field(x, 0, ts, N_SNAP, 2)
+    for _ in range(args.warmup):
+        orc.interpolate_torch(w, idx, p); orc.interpolate_torch(w, idx, u)
+    t0 = time.time()
+    for _ in range(args.steps):
+        orc.interpolate_torch(w, idx, p); orc.interpolate_torch(w, idx, u)
+    dt = (time.time() - t0) / args.steps
+    value = nc * 3 * ts / dt
+    cores = pt.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_points": int(x.shape[0]), "n_cells": int(nc), "k": 8,
+                   "fields": "p[D=1] + U[D=2]", "snapshots_per_step": ts,
+                   "note": f"each step interpolates a bounded sample of {ts} of the {N_SNAP} snapshots (linear in T)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{ts} of {N_SNAP} snapshots of p and U, oracle.interpolate_torch "
+                                   f"(export.py:446-468 strategy, torch CPU, {cores} threads)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "grid_gen_s": t_grid, "grid_gen_note": "oracle port of SamplingTree.refine on the host (no process pool)",
+        "knn_tables_s": t_knn, "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    import sparsespatialsampling_b200 as s3
+    from sparsespatialsampling_b200 import _lib
+    from sparsespatialsampling_b200.export import ExportData, KnnTables
+    from sparsespatialsampling_b200.knn import KnnIndex
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    pt.cuda.set_device(local)
+    dev = pt.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- inputs (seeded, identical on every rank)
+    x = synth.cylinder2d_cloud(N_POINTS, seed=0)
+    xd = x.to(dev)
+    metric = synth.wake_metric(xd).cpu()
+    k = 8
+
+    # ---- grid generation on rank 0 (replicas only: the loop is sequential), then broadcast grid + tables
+    grid_info, t_grid_wall = None, None
+    if rank == 0:
+        t0 = time.time()
+        sc = s3.SparseSpatialSampling(x, metric, geometries(s3.geometry), "/tmp/s3b200_bench", "c2", **{
+            "uniform_levels": GRID_KW["uniform_level"], "min_metric": GRID_KW["min_metric"]})
+        sc.execute_grid_generation()
+        pt.cuda.synchronize()
+        t_grid_wall = time.time() - t0
+        grid_info = sc.mesh_info
+        centers = sc.centers.to(dev)
+        nc = pt.tensor([centers.size(0)], device=dev)
+    else:
+        sc, centers, nc = None, None, pt.zeros(1, dtype=pt.int64, device=dev)
+    if world > 1:
+        dist.broadcast(nc, 0)
+        if rank != 0:
+            centers = pt.empty((int(nc.item()), 2), dtype=pt.float64, device=dev)
+        dist.broadcast(centers, 0)
+    n_cells = int(nc.item())
+
+    t0 = time.time()
+    index = KnnIndex(xd)
+    tables = KnnTables(index, centers, k)
+    pt.cuda.synchronize()
+    t_tables = time.time() - t0
+    if world > 1:
+        tables.broadcast_(0)            # NCCL over NVLink: every rank uses rank 0's tables
+    n_unique = int(pt.unique(tables.idx_sorted).numel())
+
+    # ---- snapshot fields of this rank's time window, resident in HBM
+    t_lo = rank * N_SNAP
+    p = synth.wake_field(xd, t_lo, t_lo + N_SNAP, N_SNAP * world, 1)
+    u = synth.wake_field(xd, t_lo, t_lo + N_SNAP, N_SNAP * world, 2)
+    out_p = pt.empty((n_cells, 1, N_SNAP), dtype=pt.float32, device=dev)
+    out_u = pt.empty((n_cells, 2, N_SNAP), dtype=pt.float32, device=dev)
+    from sparsespatialsampling_b200.interpolate import interp_gather
+
+    def step():
+        interp_gather(p, tables.idx_sorted, tables.w32_sorted, out=out_p, out_row=tables.out_row)
+        interp_gather(u, tables.idx_sorted, tables.w32_sorted, out=out_u, out_row=tables.out_row)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        pt.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = _lib.launch_count()
+    e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = pt.tensor([e0.elapsed_time(e1)], device=dev, dtype=pt.float64)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / args.steps
+    units_step = n_cells * 3 * N_SNAP * world
+    value = units_step / (ms_step * 1e-3)
+
+    # ---- end to end through the public API: host buffers in, host buffers out
+    p_h = p.cpu().pin_memory()
+    u_h = u.cpu().pin_memory()
+    res_p = pt.empty((n_cells, 1, N_SNAP), dtype=pt.float32).pin_memory()
+    res_u = pt.empty((n_cells, 2, N_SNAP), dtype=pt.float32).pin_memory()
+
+    class _Grid:
+        pass
+    g = _Grid()
+    g.n_dimensions, g.faces, g.vertices, g.levels = 2, None, None, None
+    g.centers, g.metric, g.size_initial_cell = centers, metric, 2.2
+    g.save_path, g.save_name, g.grid_name = "/tmp/s3b200_bench", f"c2_rank{rank}", "grid"
+    exp = ExportData(g, write_times=[str(i) for i in range(N_SNAP)], write_files=False, device=dev)
+    exp._tables_centers, exp._initialized_weights, exp._interpolated_metric = tables, True, True
+
+    def e2e_step():
+        exp.export(x, p_h, "p")
+        res_p.copy_(exp.interpolated_fields.centers, non_blocking=True)
+        exp.export(x, u_h, "U")
+        res_u.copy_(exp.interpolated_fields.centers, non_blocking=True)
+        pt.cuda.synchronize()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = pt.tensor([(time.time() - t0) * 1e3 / e2e_steps], device=dev, dtype=pt.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = units_step / (e2e_ms.item() * 1e-3)
+    h2d = p_h.numel() * 4 + u_h.numel() * 4
+    d2h = res_p.numel() * 4 + res_u.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (interp_gather_kernel; the step is two launches of it)
+    b_algo = algorithmic_bytes(n_unique, n_cells, k, 1, N_SNAP) + algorithmic_bytes(n_unique, n_cells, k, 2, N_SNAP)
+    achieved = b_algo / (ms_step * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("interp_gather_dram_bytes_per_step")
+
+    # ---- CPU baseline beside it: oracle port of the reference's strategy on a bounded sample, rank 0, N=1 only
+    cpu_baseline = None
+    if world == 1:
+        from oracle import s3_oracle as orc
+        ts = CPU_SAMPLE_SNAPSHOTS
+        w64 = tables.w64.cpu()
+        idx64 = tables.idx.cpu().to(pt.int64)
+        pc, uc = p_h[:, :, :ts].contiguous(), u_h[:, :, :ts].contiguous()
+        orc.interpolate_torch(w64, idx64, pc)
+        t0 = time.time()
+        reps = 3
+        for _ in range(reps):
+            orc.interpolate_torch(w64, idx64, pc); orc.interpolate_torch(w64, idx64, uc)
+        dt = (time.time() - t0) / reps
+        cores = pt.get_num_threads()
+        cpu_baseline = {"value": n_cells * 3 * ts / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{ts} of {N_SNAP} snapshots of p and U (cost is linear in T), "
+                                  f"oracle.interpolate_torch, torch CPU, {cores} threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_points": int(x.shape[0]), "n_cells": n_cells, "k": k,
+                   "fields": "p[D=1] + U[D=2]", "snapshots_per_gpu": N_SNAP, "unique_source_points": n_unique,
+                   "l2_policy": "inputs larger than L2 (1.2 GB of snapshot rows per step vs 126 MB L2)",
+                   "sharding": "snapshot window per rank; grid + KNN tables broadcast once over NCCL"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "interp_gather_kernel",
+                     "algorithmic_bytes_per_step": b_algo, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms.item(), "api": "ExportData.export(host tensors) + device->host copy of the result"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "grid_gen_s": grid_info["t_total"] if grid_info else None,
+        "grid_gen": None if grid_info is None else {
+            "t_total": grid_info["t_total"], "t_uniform": grid_info["t_uniform"], "t_adaptive": grid_info["t_adaptive"],
+            "t_geometry": grid_info["t_geometry"], "t_renumbering": grid_info["t_renumbering"],
+            "t_knn_build": grid_info["t_knn_build"], "wall_incl_setup_s": t_grid_wall,
+            "iterations": grid_info["iterations"], "n_cells": grid_info["n_cells"],
+            "captured_metric": grid_info["metric_per_iter"][-1]},
+        "knn_tables_s": t_tables,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="s3b200", choices=["s3b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

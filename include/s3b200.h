@@ -56,6 +56,10 @@ int s3_knn_predict(const s3_knn_t* h, const double* d_query, int64_t nq, int k, 
 int s3_knn_tables(const s3_knn_t* h, const double* d_query, int64_t nq, int k, int32_t* d_idx,
                   float* d_w32, double* d_w64, void* stream);
 
+/* Morton (Z-curve) ordering of a point set, used to process the sampled cells in a cache-friendly order:
+ * d_perm int32 [n] = indices of the points sorted along the curve                                  */
+int s3_morton_order(const double* d_coords, int64_t n, int dim, int32_t* d_perm, void* stream);
+
 /* ---- refinement engine (device side of SamplingTree, sparseSpatialSampling/s_cube.py) -------------
  * Cell state: structure of arrays indexed by the reference's cell index (creation order):
  *   d_center fp64 [cap, dim], d_level int32 [cap], d_lattice int32 [cap, dim] (integer position of the

@@ -437,3 +437,19 @@ class OracleTree:
         self.all_levels = np.array([self.level[c] for c in order], dtype=np.int64)[:, None]
         self.leaf_order = order
         return self
+
+
+def interpolate_torch(weights, idx, data, chunk_size: int = 100000):
+    """
+    The reference's CPU evaluation strategy for interpolate_data (export.py:446-468) with torch CPU operators
+    (all intra-op threads): gather the k source rows of a chunk of cells, multiply by the weights, reduce over k.
+    Used as the timed CPU baseline (bench.py) -- same temporaries, same threading model as the reference.
+    """
+    import torch as pt
+    nc, k = idx.shape
+    out = pt.empty((nc, data.shape[1], data.shape[2]), dtype=weights.dtype)
+    for s in range(0, nc, chunk_size):
+        e = min(s + chunk_size, nc)
+        rows = data.index_select(0, idx[s:e].reshape(-1)).reshape(e - s, k, data.shape[1], data.shape[2])
+        out[s:e] = (rows * weights[s:e].reshape(e - s, k, 1, 1)).sum(dim=1)
+    return out

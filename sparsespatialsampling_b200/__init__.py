@@ -12,10 +12,12 @@ from .sparse_spatial_sampling import SparseSpatialSampling, list_geometries
 from .s_cube import SamplingTree
 from .interpolate import interpolate_data, interp_gather
 from .knn import KnnIndex
+from .export import ExportData, Fields
+from .data import Datawriter
 from . import geometry
 
 _logging.getLogger(__name__).addHandler(_logging.NullHandler())
 
 __version__ = "0.1.0"
 __all__ = ["SparseSpatialSampling", "SamplingTree", "list_geometries", "interpolate_data", "interp_gather", "KnnIndex",
-           "geometry"]
+           "ExportData", "Fields", "Datawriter", "geometry"]

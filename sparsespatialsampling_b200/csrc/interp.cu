@@ -168,6 +168,7 @@ static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, 
                 reinterpret_cast<const Tin*>(data), row_len, idx_p, w_p, cells_here, k, orow_p, out_p);
         }
         S3_LAUNCH_CHECK();
+        note_launch(1);
     }
     return S3_OK;
 }

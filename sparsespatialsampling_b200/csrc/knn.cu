@@ -205,6 +205,7 @@ static int launch_query(const KnnIndex& ix, const double* query, int64_t nq, int
         knn_query_kernel<3, MODE><<<(unsigned)blocks, kQueryWarps * 32, 0, stream>>>(v, query, nq, k, out_idx, out_dist,
                                                                                     out_pred, tab_idx, tab_w32, tab_w64);
     S3_LAUNCH_CHECK();
+    note_launch(1);
     return S3_OK;
 }
 
@@ -270,6 +271,7 @@ static int knn_build_impl(const double* coords, int64_t n, int dim, const double
     S3_CUDA(cudaMemcpyAsync(hbb, bb, sizeof(double) * 2 * dim, cudaMemcpyDeviceToHost, stream));
     S3_CUDA(cudaStreamSynchronize(stream));
     for (int a = 0; a < dim; ++a) { ix->bb_lo[a] = hbb[a]; ix->bb_hi[a] = hbb[dim + a]; }
+    note_launch(28 + L);
     return S3_OK;
 }
 
@@ -339,7 +341,36 @@ int s3_knn_tables(const s3_knn_t* h, const double* d_query, int64_t nq, int k, i
     return launch_query<2>(h->ix, d_query, nq, k, nullptr, nullptr, nullptr, d_idx, d_w32, d_w64, (cudaStream_t)stream);
 }
 
+int s3_morton_order(const double* d_coords, int64_t n, int dim, int32_t* d_perm, void* stream) {
+    S3_REQUIRE(d_coords && d_perm, "s3_morton_order: NULL argument");
+    S3_REQUIRE(dim == 2 || dim == 3, "s3_morton_order: dim must be 2 or 3");
+    S3_REQUIRE(n >= 0 && n < ((int64_t)1 << 31), "s3_morton_order: n out of range");
+    if (n == 0) return S3_OK;
+    cudaStream_t st_ = (cudaStream_t)stream;
+    Scratch scratch(st_);
+    const int nparts = (int)(ceil_div(n, 256) < 1024 ? ceil_div(n, 256) : 1024);
+    double *partial = nullptr, *bb = nullptr;
+    uint64_t *ka = nullptr, *kb = nullptr;
+    uint32_t *va = nullptr, *vb = nullptr;
+    S3_TRY(scratch.alloc(&partial, (size_t)nparts * 2 * dim));
+    S3_TRY(scratch.alloc(&bb, 2 * dim));
+    S3_TRY(scratch.alloc(&ka, n));
+    S3_TRY(scratch.alloc(&kb, n));
+    S3_TRY(scratch.alloc(&va, n));
+    S3_TRY(scratch.alloc(&vb, n));
+    bbox_partial_kernel<<<nparts, 256, 0, st_>>>(d_coords, n, dim, partial);
+    bbox_final_kernel<<<1, 32, 0, st_>>>(partial, nparts, dim, bb);
+    morton_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st_>>>(d_coords, n, dim, bb, ka, va);
+    S3_LAUNCH_CHECK();
+    bool in_a = true;
+    S3_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, 64, st_, &in_a));
+    S3_CUDA(cudaMemcpyAsync(d_perm, in_a ? va : vb, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st_));
+    note_launch(27);
+    return S3_OK;
+}
+
 }  // extern "C"
+
 
 namespace s3 {
 const KnnIndex* knn_index_of(const s3_knn_t* h) { return h ? &h->ix : nullptr; }

@@ -1,0 +1,302 @@
+"""
+Export stage of S^3 on the GPU: interpolate original snapshots onto the sampled grid and hand them to the writer.
+
+``ExportData`` keeps the constructor, ``export(coordinates, data, field_name, n_snapshots_total, chunk_size)``, the
+batch-wise calling convention and the properties of the reference class (sparseSpatialSampling/export.py:40-444).
+What changes is where the work happens:
+
+* the KNN cache (``_build_knn_cache``, export.py:403-444) is built by the device KNN index; the (idx, w) tables stay
+  resident in HBM, stored in Morton order of the cell centres so that cells handled by one CTA share source rows;
+* ``interpolate_data`` (export.py:446-468) is one launch of the gather kernel per field batch -- no ``data[idx]``
+  temporary, hence no chunking over cells (``chunk_size`` is accepted and ignored);
+* host tensors are staged through pinned memory; CUDA tensors are accepted as they are (the reference rejects them,
+  export.py:160-161).
+Interpolated fields are fp32 by default (fp32 snapshots in, fp32 FMA accumulation; within 1e-5 relative of the
+reference's fp64 result); ``out_dtype=torch.float64`` reproduces the reference's dtype with fp64 accumulation.
+"""
+import logging
+from os import makedirs, path
+from time import time
+from typing import Union
+
+import torch as pt
+
+from . import _lib
+from .const import GRID, CONST, FACES, CENTERS, VERTICES, DATA
+from .data import Datawriter
+from .interpolate import interp_gather
+from .knn import KnnIndex, default_n_neighbors
+
+logger = logging.getLogger(__name__)
+
+
+class Fields:
+    def __init__(self, centers: pt.Tensor = None, vertices: pt.Tensor = None):
+        self.centers = centers
+        self.vertices = vertices
+
+
+class KnnTables:
+    """Device-resident KNN cache of one query set (cell centres or vertices)."""
+
+    def __init__(self, index: KnnIndex, query: pt.Tensor, k: int):
+        lib = _lib.load()
+        dev = index.device
+        q = query.detach().to(device=dev, dtype=pt.float64).contiguous()
+        idx, w32, w64 = index.tables(q, k)
+        # processing order: Morton order of the query points
+        perm = pt.empty((q.size(0),), dtype=pt.int32, device=dev)
+        with pt.cuda.device(dev):
+            _lib.check(lib.s3_morton_order(_lib.ptr(q), q.size(0), q.size(1), _lib.ptr(perm), _lib.stream_ptr()))
+        p64 = perm.to(pt.int64)
+        self.idx = idx                       # original order (reference-compatible view)
+        self.w64 = w64
+        self.idx_sorted = idx[p64].contiguous()
+        self.w32_sorted = w32[p64].contiguous()
+        self.w64_sorted = w64[p64].contiguous()
+        self.out_row = perm.contiguous()
+        self.n = q.size(0)
+        self.k = k
+
+    def interpolate(self, data: pt.Tensor, out_dtype) -> pt.Tensor:
+        w = self.w32_sorted if out_dtype == pt.float32 else self.w64_sorted
+        out = pt.empty((self.n,) + tuple(data.shape[1:]), dtype=out_dtype, device=data.device)
+        return interp_gather(data, self.idx_sorted, w, out=out, out_row=self.out_row, out_dtype=out_dtype)
+
+    def broadcast_(self, src: int = 0):
+        """Share the tables of rank ``src`` with all ranks (NCCL over NVLink; one-off before the export loop)."""
+        import torch.distributed as dist
+        for t in (self.idx_sorted, self.w32_sorted, self.w64_sorted, self.out_row):
+            dist.broadcast(t, src=src)
+        return self
+
+
+class ExportData:
+    def __init__(self, s_cube, write_new_file_for_each_field: bool = False, n_jobs: int = None,
+                 n_neighbors: int = None, interpolate_at_vertices: bool = False, write_times: Union[list, str] = None,
+                 append_existing: bool = False, out_dtype=None, device=None, write_files: bool = True):
+        _lib.require_cuda()
+        self._device = pt.device(device) if device is not None else pt.device("cuda", pt.cuda.current_device())
+        self._interpolate_at_vertices = interpolate_at_vertices
+        self._new_file = write_new_file_for_each_field
+        self._out_dtype = out_dtype
+        self._write_files = write_files
+
+        # grid properties taken from the s_cube object (export.py:74-83)
+        self.n_dimensions = s_cube.n_dimensions
+        self._face_id = s_cube.faces
+        self._centers = s_cube.centers
+        self._vertices = s_cube.vertices
+        self._levels = s_cube.levels
+        self._metric = s_cube.metric
+        self._size_initial_cell = s_cube.size_initial_cell
+        self._save_dir = s_cube.save_path
+        self._save_name = s_cube.save_name
+        self._grid_name = s_cube.grid_name
+
+        if write_times is not None:
+            self._write_times = write_times if isinstance(write_times, list) else [write_times]
+        else:
+            self._write_times = None
+            logger.warning("Argument ``write_times`` is ``None``. Make sure to set the ``write_times`` before calling "
+                           "the ``export()`` method.")
+
+        self._interpolated_fields = Fields()
+        self._field_name = None
+        self._datawriter = None
+        self._snapshot_counter = 0
+        self._initialized_hdf5 = False if not append_existing else True
+        self._interpolated_metric = False if not append_existing else True
+        self._initialized_weights = False
+        self._finished = False
+        self._n_snapshots_total = None
+        self._t_start = time()
+        if append_existing:
+            logger.info(f"Appending fields to file {path.join(self._save_dir, self._save_name)}.h5")
+            if self._new_file:
+                logger.warning("Setting `write_new_file_for_each_field = False` since `append_existing` is `True`")
+                self._new_file = False
+
+        if n_neighbors is None:
+            n_neighbors = default_n_neighbors(self.n_dimensions)
+        self._n_neighbors = n_neighbors
+        self._n_jobs = n_jobs                    # accepted and ignored
+        self._tables_centers = None
+        self._tables_vertices = None
+        self._coord_shape = None
+        self._chunk_size = None
+        self.metric_on_grid = None
+
+    # ------------------------------------------------------------------------------------------ public
+    def export(self, coordinates: pt.Tensor, data: pt.Tensor, field_name: str, n_snapshots_total: int = None,
+               chunk_size: int = 100000) -> None:
+        if self._write_times is None:
+            raise ValueError("Couldn't find any ``write_times`` for export. Make sure to pass the write times "
+                             "when instantiating the export object or set it before calling the ``export method``.")
+        self._chunk_size = int(chunk_size)
+        self._field_name = field_name
+        self._fit_data(coordinates, data, field_name, n_snapshots_total)
+        self._write_data()
+
+    @property
+    def interpolated_fields(self) -> Fields:
+        """Result of the last ``export`` call (device tensors ``[Nc, D, T_batch]``)."""
+        return self._last_fields
+
+    # ------------------------------------------------------------------------------------------ internals
+    def _fit_data(self, _coord, _data, _field_name, _n_snapshots_total=None) -> None:
+        # export.py:169-231
+        if len(_data.size()) < 2:
+            raise ValueError("The provided field must have the shape '[N_cells, N_dimensions, N_snapshots]' for a "
+                             "vector field and '[N_cells, 1, N_snapshots]' for a scalar field. "
+                             f"Found a dimension of {len(_data.size())} for parameter 'data'.")
+        elif len(_data.size()) == 2:
+            logger.warning("Detected a scalar field of dimension 2 as input. Reshaping to '[N_cells, 1, N_snapshots]'.")
+            _data = _data.unsqueeze(1)
+        if not self._initialized_weights:
+            self._build_knn_cache(_coord)
+        if self._snapshot_counter == 0:
+            logger.info(f"Starting interpolation and export of field {self._field_name}.")
+        if not self._interpolated_metric:
+            # metric on the sampled grid (export.py:214-216), fp64
+            m = self._metric.detach().to(device=self._device, dtype=pt.float64).reshape(-1, 1).contiguous()
+            self._metric = self._tables_centers.interpolate(m, pt.float64).reshape(-1).cpu()
+            self.metric_on_grid = self._metric
+            self._interpolated_metric = True
+        if self._snapshot_counter == 0:
+            self._n_snapshots_total = _n_snapshots_total if _n_snapshots_total is not None else _data.size(-1)
+
+        d = self._stage(_data)
+        out_dtype = self._out_dtype
+        if out_dtype is None:
+            out_dtype = pt.float32 if d.dtype == pt.float32 else pt.float64
+        self._interpolated_fields.centers = self._tables_centers.interpolate(d, out_dtype)
+        if self._interpolate_at_vertices:
+            self._interpolated_fields.vertices = self._tables_vertices.interpolate(d, out_dtype)
+        self._last_fields = Fields(self._interpolated_fields.centers, self._interpolated_fields.vertices)
+        self._snapshot_counter += _data.size(-1)
+
+    def _stage(self, data: pt.Tensor) -> pt.Tensor:
+        """Host -> device copy of one snapshot batch (pinned staging for pageable host tensors)."""
+        if data.dtype not in (pt.float32, pt.float64):
+            data = data.to(pt.float32)
+        if data.is_cuda:
+            return data.to(self._device).contiguous()
+        data = data.contiguous()
+        if not data.is_pinned():
+            try:
+                data = data.pin_memory()
+            except RuntimeError:
+                pass
+        return data.to(self._device, non_blocking=True)
+
+    def _build_knn_cache(self, _coord: pt.Tensor) -> None:
+        # export.py:403-444
+        logger.info("Initializing KNN and computing interpolation weights.")
+        if self._coord_shape is not None and _coord.shape != self._coord_shape:
+            logger.warning("CFD grid change detected. Re-computing interpolation weights of the KNN.")
+        self._coord_shape = _coord.shape
+        index = KnnIndex(_coord, device=self._device)
+        self._tables_centers = KnnTables(index, self._centers, self._n_neighbors)
+        if self._interpolate_at_vertices:
+            self._tables_vertices = KnnTables(index, self._vertices, self._n_neighbors)
+        self._initialized_weights = True
+        del index
+
+    # reference-compatible views of the cache
+    @property
+    def _knn_idx_centers(self):
+        return None if self._tables_centers is None else self._tables_centers.idx
+
+    @property
+    def _knn_w_centers(self):
+        return None if self._tables_centers is None else self._tables_centers.w64
+
+    def _write_data(self) -> None:
+        # export.py:233-319
+        if not self._write_files:
+            if self._snapshot_counter == self._n_snapshots_total:
+                self._interpolated_fields = Fields()
+                self._snapshot_counter = 0
+            return
+        if not self._initialized_hdf5:
+            logger.info(f"Writing HDF5 file for field {self._field_name}.")
+            if not path.exists(self._save_dir):
+                makedirs(self._save_dir)
+            name = f"{self._save_name}_{self._field_name}.h5" if self._new_file else f"{self._save_name}.h5"
+            self._datawriter = Datawriter(self._save_dir, name)
+            self._datawriter.write_data(FACES, group=GRID, data=self._face_id)
+            self._datawriter.write_data(VERTICES, group=GRID, data=self._vertices)
+            self._datawriter.write_data(CENTERS, group=GRID, data=self._centers)
+            self._datawriter.write_data("levels", group=CONST, data=self._levels)
+            self._datawriter.write_data("metric", group=CONST, data=self._metric)
+            self._datawriter.write_data("size_initial_cell", group=CONST, data=self._size_initial_cell)
+            self._initialized_hdf5 = True
+            self._levels = None
+            self._metric = None
+            self._size_initial_cell = None
+        else:
+            if not self._new_file and self._datawriter is None:
+                self._datawriter = Datawriter(self._save_dir, f"{self._save_name}.h5", mode="a")
+            else:
+                self._datawriter.mode = "a"
+
+        centers = self._interpolated_fields.centers.cpu()
+        vertices = self._interpolated_fields.vertices.cpu() if self._interpolate_at_vertices else None
+        t_start = self._snapshot_counter - centers.size(-1)
+        t_end = self._snapshot_counter
+        for i, t in enumerate(self._write_times[t_start:t_end]):
+            if centers.size(1) == 1:
+                self._datawriter.write_data(f"{self._field_name}_center", group=DATA, time_step=str(t),
+                                            data=centers.squeeze(1)[:, i])
+                if vertices is not None:
+                    self._datawriter.write_data(f"{self._field_name}_vertices", group=DATA, time_step=str(t),
+                                                data=vertices.squeeze(1)[:, i])
+            else:
+                self._datawriter.write_data(f"{self._field_name}_center", group=DATA, time_step=str(t),
+                                            data=centers[:, :, i])
+                if vertices is not None:
+                    self._datawriter.write_data(f"{self._field_name}_vertices", group=DATA, time_step=str(t),
+                                                data=vertices[:, :, i])
+        if self._snapshot_counter == self._n_snapshots_total:
+            self._datawriter.close()
+            self._datawriter.write_xdmf_file()
+            self._interpolated_fields = Fields()
+            self._snapshot_counter = 0
+            if self._new_file:
+                self._initialized_hdf5 = False
+            logger.info(f"Finished export of field {self._field_name} in {round(time() - self._t_start, 3)}s.")
+            self._t_start = time()
+
+    # ------------------------------------------------------------------------------------------ properties
+    @property
+    def write_times(self) -> list:
+        return self._write_times
+
+    @write_times.setter
+    def write_times(self, value: Union[str, list]) -> None:
+        self._write_times = value if isinstance(value, list) else [value]
+
+    @property
+    def new_file(self) -> bool:
+        return self._new_file
+
+    @property
+    def save_name(self) -> str:
+        return self._save_name
+
+    @save_name.setter
+    def save_name(self, new_name: str) -> None:
+        self._save_name = new_name
+        self._initialized_hdf5 = False
+
+    @property
+    def save_dir(self) -> str:
+        return self._save_dir
+
+    @save_dir.setter
+    def save_dir(self, new_path: str) -> None:
+        self._save_dir = new_path
+        self._initialized_hdf5 = False
+        if not path.exists(self._save_dir):
+            makedirs(self._save_dir)
