@@ -241,11 +241,13 @@ def run_ours(args):
     e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
+        pt.cuda.profiler.start()        # no-op unless run under `ncu --profile-from-start off`
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         barrier()
+        pt.cuda.profiler.stop()
     ms = pt.tensor([e0.elapsed_time(e1)], device=dev, dtype=pt.float64)
     launches = _lib.launch_count() - launches0
     if world > 1:

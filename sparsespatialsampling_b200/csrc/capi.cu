@@ -16,6 +16,20 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+void configure_mempool_once() {
+    static std::atomic<uint32_t> done_mask{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
+    const uint32_t bit = 1u << dev;
+    if (done_mask.load(std::memory_order_acquire) & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done_mask.fetch_or(bit, std::memory_order_release);
+}
+
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace s3

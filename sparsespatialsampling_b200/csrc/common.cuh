@@ -14,6 +14,8 @@ namespace s3 {
 
 void set_error(const char* fmt, ...);
 void note_launch(int n);
+// keep stream-ordered scratch memory cached in the pool across synchronisations (default: released)
+void configure_mempool_once();
 
 #define S3_CUDA(call)                                                                   \
     do {                                                                                \
@@ -50,7 +52,7 @@ struct Scratch {
     cudaStream_t stream;
     void* ptrs[32];
     int n = 0;
-    explicit Scratch(cudaStream_t s) : stream(s) {}
+    explicit Scratch(cudaStream_t s) : stream(s) { configure_mempool_once(); }
     ~Scratch() {
         for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], stream);
     }
