@@ -225,9 +225,11 @@ def run_ours(args):
     out_u = pt.empty((n_cells, 2, N_SNAP), dtype=pt.float32, device=dev)
     from sparsespatialsampling_b200.interpolate import interp_gather
 
+    tables.mode, tables.chunk_cols = args.kernel, args.chunk_cols
+
     def step():
-        interp_gather(p, tables.idx_sorted, tables.w32_sorted, out=out_p, out_row=tables.out_row)
-        interp_gather(u, tables.idx_sorted, tables.w32_sorted, out=out_u, out_row=tables.out_row)
+        tables.interpolate(p, pt.float32, out=out_p)
+        tables.interpolate(u, pt.float32, out=out_u)
 
     def barrier():
         if world > 1:
@@ -333,9 +335,11 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "n_points": int(x.shape[0]), "n_cells": n_cells, "k": k,
                    "fields": "p[D=1] + U[D=2]", "snapshots_per_gpu": N_SNAP, "unique_source_points": n_unique,
                    "l2_policy": "inputs larger than L2 (1.2 GB of snapshot rows per step vs 126 MB L2)",
-                   "sharding": "snapshot window per rank; grid + KNN tables broadcast once over NCCL"},
+                   "sharding": "snapshot window per rank; grid + KNN tables broadcast once over NCCL",
+                   "kernel": args.kernel, "chunk_cols": args.chunk_cols,
+                   "unique_rows_per_tile_sum": tables.tiles.total_rows if tables.tiles is not None else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "interp_gather_kernel",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "interp_staged_kernel" if args.kernel == "staged" else "interp_gather_kernel",
                      "algorithmic_bytes_per_step": b_algo, "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -362,6 +366,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="s3b200", choices=["s3b200", "reference"])
+    ap.add_argument("--kernel", default="staged", choices=["staged", "direct"], help="interpolation kernel variant")
+    ap.add_argument("--chunk-cols", type=int, default=256, choices=[128, 256], help="columns staged per CTA")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

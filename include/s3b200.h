@@ -132,6 +132,22 @@ int s3_interp_gather(const void* d_data, int data_dtype, int64_t n_src, int64_t 
                      const int32_t* d_idx, const void* d_w, int64_t n_cells, int k,
                      const int32_t* d_out_row, void* d_out, int out_dtype, void* stream);
 
+/* Staged fp32 variant of the same operator: cells are grouped in tiles of 32 (processing order); the
+ * unique source rows of a tile are copied once into shared memory by TMA bulk copies and re-used by
+ * all cells of the tile.
+ * s3_interp_tiles_build (once per KNN cache): from d_idx int32 [n_cells, k] (processing order) builds
+ *   d_tile_rows int32 [n_tiles, 32*k] (unique rows, ascending), d_tile_nrows int32 [n_tiles],
+ *   d_tile_lidx uint16 [n_tiles, 32*k] (position of every reference in its tile's row list).
+ * s3_interp_staged: d_w fp32 [n_tiles*32, k] (zero padded to full tiles); max_rows = largest entry of
+ *   d_tile_nrows (sizes the staging buffer; larger tiles fall back to direct loads);
+ *   chunk_cols = 128 | 256 columns staged per CTA. Requires row_len % 4 == 0.                        */
+int s3_interp_tiles_build(const int32_t* d_idx, int64_t n_cells, int k, int32_t* d_tile_rows,
+                          int32_t* d_tile_nrows, uint16_t* d_tile_lidx, void* stream);
+int s3_interp_staged(const float* d_data, int64_t n_src, int64_t row_len, const int32_t* d_tile_rows,
+                     const int32_t* d_tile_nrows, const uint16_t* d_tile_lidx, const float* d_w,
+                     int64_t n_cells, int k, int max_rows, int chunk_cols, const int32_t* d_out_row,
+                     float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

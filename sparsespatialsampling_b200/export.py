@@ -24,7 +24,7 @@ import torch as pt
 from . import _lib
 from .const import GRID, CONST, FACES, CENTERS, VERTICES, DATA
 from .data import Datawriter
-from .interpolate import interp_gather
+from .interpolate import interp_gather, StagedTiles
 from .knn import KnnIndex, default_n_neighbors
 
 logger = logging.getLogger(__name__)
@@ -57,10 +57,18 @@ class KnnTables:
         self.out_row = perm.contiguous()
         self.n = q.size(0)
         self.k = k
+        self.tiles = StagedTiles(self.idx_sorted, self.w32_sorted) if 32 * k <= 2048 else None
+        self.mode = "staged"          # "staged" (TMA-staged tiles, fp32) or "direct"
+        self.chunk_cols = 256
 
-    def interpolate(self, data: pt.Tensor, out_dtype) -> pt.Tensor:
+    def interpolate(self, data: pt.Tensor, out_dtype, out: pt.Tensor = None) -> pt.Tensor:
+        if out is None:
+            out = pt.empty((self.n,) + tuple(data.shape[1:]), dtype=out_dtype, device=data.device)
+        row_len = data.numel() // max(data.size(0), 1)
+        if (self.mode == "staged" and self.tiles is not None and out_dtype == pt.float32 and
+                data.dtype == pt.float32 and row_len % 4 == 0):
+            return self.tiles.interpolate(data, out=out, out_row=self.out_row, chunk_cols=self.chunk_cols)
         w = self.w32_sorted if out_dtype == pt.float32 else self.w64_sorted
-        out = pt.empty((self.n,) + tuple(data.shape[1:]), dtype=out_dtype, device=data.device)
         return interp_gather(data, self.idx_sorted, w, out=out, out_row=self.out_row, out_dtype=out_dtype)
 
     def broadcast_(self, src: int = 0):
@@ -68,6 +76,8 @@ class KnnTables:
         import torch.distributed as dist
         for t in (self.idx_sorted, self.w32_sorted, self.w64_sorted, self.out_row):
             dist.broadcast(t, src=src)
+        if self.tiles is not None:
+            self.tiles = StagedTiles(self.idx_sorted, self.w32_sorted)
         return self
 
 

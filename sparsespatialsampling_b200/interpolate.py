@@ -66,3 +66,46 @@ def interpolate_data(weights: pt.Tensor, idx_weights: pt.Tensor, data: pt.Tensor
         d = d.to(pt.float64 if out_dtype == pt.float64 else pt.float32)
     out = interp_gather(d, i, w, out_dtype=out_dtype)
     return out if src_device.type == "cuda" else out.to(src_device)
+
+
+class StagedTiles:
+    """
+    Tile structures of the staged interpolation kernel (``s3_interp_tiles_build`` / ``s3_interp_staged``): for every
+    tile of 32 consecutive cells (processing order) the ascending list of unique source rows and the position of
+    every (cell, neighbour) reference in it. Built once per KNN cache.
+    """
+    TILE = 32
+
+    def __init__(self, idx_sorted: pt.Tensor, w32_sorted: pt.Tensor):
+        _lib.require_cuda()
+        lib = _lib.load()
+        dev = idx_sorted.device
+        self.n_cells, self.k = idx_sorted.shape
+        self.n_tiles = (self.n_cells + self.TILE - 1) // self.TILE
+        cap = self.TILE * self.k
+        self.rows = pt.empty((max(self.n_tiles, 1), cap), dtype=pt.int32, device=dev)
+        self.nrows = pt.zeros((max(self.n_tiles, 1),), dtype=pt.int32, device=dev)
+        self.lidx = pt.empty((max(self.n_tiles, 1), cap), dtype=pt.uint16, device=dev)
+        self.w = pt.zeros((max(self.n_tiles, 1) * self.TILE, self.k), dtype=pt.float32, device=dev)
+        self.w[:self.n_cells] = w32_sorted
+        with pt.cuda.device(dev):
+            _lib.check(lib.s3_interp_tiles_build(_lib.ptr(idx_sorted.contiguous()), self.n_cells, self.k,
+                                                 _lib.ptr(self.rows), _lib.ptr(self.nrows), _lib.ptr(self.lidx),
+                                                 _lib.stream_ptr()))
+        self.max_rows = int(self.nrows.max().item()) if self.n_tiles else 1
+        self.total_rows = int(self.nrows.sum().item()) if self.n_tiles else 0
+
+    def interpolate(self, data: pt.Tensor, out: pt.Tensor = None, out_row: pt.Tensor = None,
+                    chunk_cols: int = 256) -> pt.Tensor:
+        lib = _lib.load()
+        assert data.is_cuda and data.dtype == pt.float32
+        data = data.contiguous()
+        n_src = data.size(0)
+        row_len = data.numel() // max(n_src, 1)
+        if out is None:
+            out = pt.empty((self.n_cells,) + tuple(data.shape[1:]), dtype=pt.float32, device=data.device)
+        with pt.cuda.device(data.device):
+            _lib.check(lib.s3_interp_staged(_lib.ptr(data), n_src, row_len, _lib.ptr(self.rows), _lib.ptr(self.nrows),
+                                            _lib.ptr(self.lidx), _lib.ptr(self.w), self.n_cells, self.k, self.max_rows,
+                                            int(chunk_cols), _lib.ptr(out_row), _lib.ptr(out), _lib.stream_ptr()))
+        return out

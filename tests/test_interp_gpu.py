@@ -73,3 +73,43 @@ def test_reference_signature_interpolate_data(cuda):
     out = interpolate_data(pt.from_numpy(w), pt.from_numpy(idx.astype(np.int64)), pt.from_numpy(data), 100)
     assert out.dtype == pt.float64 and not out.is_cuda
     assert np.array_equal(out.numpy(), orc.interpolate(w, idx.astype(np.int64), data))
+
+
+@pytest.mark.parametrize("N,Nc,k,D,T,chunk", [
+    (5000, 1777, 8, 1, 1000, 256), (5000, 1000, 8, 2, 500, 128), (3000, 515, 26, 3, 64, 256), (2000, 33, 26, 1, 8, 128),
+    (100, 1, 8, 1, 4, 256), (4000, 2049, 5, 1, 128, 128), (60000, 3000, 26, 1, 260, 256),
+])
+def test_staged_kernel_equals_direct_kernel(cuda, N, Nc, k, D, T, chunk):
+    # the TMA-staged kernel accumulates in the same order as the direct one -> bit-identical fp32 results,
+    # and both are within the stated tolerance of the oracle
+    from sparsespatialsampling_b200.interpolate import interp_gather, StagedTiles
+    data, idx, w = _case(N, Nc, k, D, T, N + Nc + k)
+    if N == 60000:                                   # scattered references: more unique rows than the staging buffer
+        pass
+    else:                                            # clustered references: heavy row sharing inside a tile
+        base = (np.arange(Nc)[:, None] * 3) % max(N - 64, 1)
+        idx = (base + np.random.default_rng(1).integers(0, 48, (Nc, k))).astype(np.int32)
+    d = pt.from_numpy(data).cuda()
+    i = pt.from_numpy(idx).cuda()
+    wt = pt.from_numpy(w).float().cuda()
+    direct = interp_gather(d, i, wt)
+    tiles = StagedTiles(i, wt)
+    staged = tiles.interpolate(d, chunk_cols=chunk)
+    assert pt.equal(staged, direct)
+    ref = orc.interpolate(w, idx.astype(np.int64), data)
+    scale = np.abs(data[idx]).max(axis=1)
+    assert (np.abs(staged.cpu().numpy() - ref) <= RTOL_F32 * np.maximum(scale, 1e-30)).all()
+    # permuted destination rows
+    perm = pt.randperm(Nc, device="cuda").to(pt.int32)
+    out = pt.zeros_like(direct)
+    tiles.interpolate(d, out=out, out_row=perm, chunk_cols=chunk)
+    assert pt.equal(out[perm.long()], direct)
+    # tile tables: every reference resolves to its source row
+    rows = tiles.rows.cpu().numpy().reshape(tiles.n_tiles, -1)
+    lidx = tiles.lidx.cpu().numpy().astype(np.int64).reshape(tiles.n_tiles, 32, k)
+    for t in range(0, tiles.n_tiles, max(1, tiles.n_tiles // 7)):
+        nc = min(32, Nc - 32 * t)
+        got = rows[t][lidx[t, :nc]]
+        assert np.array_equal(got, idx[32 * t:32 * t + nc])
+        nr = int(tiles.nrows[t])
+        assert np.array_equal(rows[t][:nr], np.unique(idx[32 * t:32 * t + nc]))
