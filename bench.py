@@ -226,6 +226,18 @@ def run_ours(args):
     from sparsespatialsampling_b200.interpolate import interp_gather
 
     tables.mode, tables.chunk_cols = args.kernel, args.chunk_cols
+    if args.staging >= 0:
+        _lib.check(_lib.load().s3_set_tuning(1, args.staging))
+    if args.stage_kb:
+        _lib.check(_lib.load().s3_set_tuning(2, args.stage_kb))
+    if args.variant >= 0:
+        _lib.check(_lib.load().s3_set_tuning(3, args.variant))
+    if args.warps:
+        _lib.check(_lib.load().s3_set_tuning(4, args.warps))
+    if args.unroll:
+        _lib.check(_lib.load().s3_set_tuning(5, args.unroll))
+    if args.cells_per_cta:
+        _lib.check(_lib.load().s3_set_tuning(0, args.cells_per_cta))
 
     def step():
         tables.interpolate(p, pt.float32, out=out_p)
@@ -366,7 +378,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="s3b200", choices=["s3b200", "reference"])
-    ap.add_argument("--kernel", default="staged", choices=["staged", "direct"], help="interpolation kernel variant")
+    ap.add_argument("--kernel", default="direct", choices=["staged", "direct"], help="interpolation kernel variant")
+    ap.add_argument("--cells-per-cta", type=int, default=0, help="direct kernel: cells per CTA (0 = library default)")
+    ap.add_argument("--staging", type=int, default=-1, help="staged kernel: 0 = TMA bulk copies, 1 = cp.async")
+    ap.add_argument("--stage-kb", type=int, default=0, help="staged kernel: shared-memory budget per CTA in KB")
+    ap.add_argument("--variant", type=int, default=-1, help="direct kernel: 0 = CTA walks cells, 1 = warp per cell")
+    ap.add_argument("--warps", type=int, default=0, help="warp-per-cell kernel: warps (= cells) per CTA")
+    ap.add_argument("--unroll", type=int, default=0, help="warp-per-cell kernel: column vectors per lane and step")
     ap.add_argument("--chunk-cols", type=int, default=256, choices=[128, 256], help="columns staged per CTA")
     args = ap.parse_args()
     if args.impl == "reference":

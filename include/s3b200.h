@@ -35,6 +35,9 @@ int s3_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t s3_launch_count(void);
 
+/* tuning knobs (benchmarking): key 0 = cells per CTA of the direct interpolation kernel */
+int s3_set_tuning(int key, int value);
+
 /* ---- k-nearest-neighbour index over the original point cloud ---------------------------------
  * replaces sklearn KNeighborsRegressor / NearestNeighbors as used in
  *   sparseSpatialSampling/s_cube.py:161-163 (fit), :224, :328, :372 (predict)

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "s3_last_error": (c_char_p, []),
     "s3_version": (c_int, []),
     "s3_launch_count": (c_int64, []),
+    "s3_set_tuning": (c_int, [c_int, c_int]),
     "s3_knn_build": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
     "s3_knn_free": (c_int, [c_void_p]),
     "s3_knn_query": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

@@ -15,8 +15,14 @@
 
 namespace s3 {
 
+extern int g_staging;
+extern int g_stage_budget_kb;
 constexpr int kInterpThreads = 128;
-constexpr int kCellsPerCta = 32;
+constexpr int kMaxCellsPerCta = 32;
+static int g_cells_per_cta = 4;
+static int g_direct_variant = 1;   // 0 = CTA walks cells, 1 = warp per cell (s3_set_tuning key 3)
+static int g_warps_per_cta = 8;
+static int g_unroll = 2;           // column vectors per lane and step (s3_set_tuning key 5)    // warp-per-cell variant (s3_set_tuning key 4)   // tuning knob (s3_set_tuning key 0)
 
 template <typename T, int V>
 struct alignas(sizeof(T) * V) Vec {
@@ -35,13 +41,13 @@ template <typename Tin, typename Tw, typename Tout, int V, int MODE>
 __global__ void __launch_bounds__(kInterpThreads)
 interp_gather_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
                      const Tw* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
-                     Tout* __restrict__ out) {
+                     Tout* __restrict__ out, int kCellsPerCta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* s_idx = reinterpret_cast<int32_t*>(smem_raw);
     Tw* s_w = reinterpret_cast<Tw*>(smem_raw + ((sizeof(int32_t) * kCellsPerCta * k + 15) / 16) * 16);
     __shared__ __align__(8) uint64_t bar;
 
-    const int64_t cell0 = (int64_t)blockIdx.y * kCellsPerCta;
+    const int64_t cell0 = (int64_t)blockIdx.x * kCellsPerCta;
     const int ncell = (int)((n_cells - cell0) < kCellsPerCta ? (n_cells - cell0) : kCellsPerCta);
     const uint32_t bytes_idx = (uint32_t)(sizeof(int32_t) * ncell * k);
     const uint32_t bytes_w = (uint32_t)(sizeof(Tw) * ncell * k);
@@ -66,7 +72,7 @@ interp_gather_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_
         __syncthreads();
     }
 
-    const int64_t col = ((int64_t)blockIdx.x * kInterpThreads + threadIdx.x) * V;
+    const int64_t col = ((int64_t)blockIdx.y * kInterpThreads + threadIdx.x) * V;
     if (col >= row_len) return;
     const Tin* dcol = data + col;
 
@@ -108,44 +114,149 @@ interp_gather_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_
     }
 }
 
+// Warp-per-cell variant: the warps of a CTA work on CONSECUTIVE cells (Morton neighbours) and sweep the row in
+// lock step, 128 columns (one 128-bit vector per lane) at a time. Neighbouring cells share most of their source
+// rows, so the same 512-byte row segments are requested by several warps of the CTA within a few hundred cycles
+// and are served by L1 (hit or hit-under-miss) instead of crossing L2->SM once per reference; the CTAs in flight
+// cover a compact window of the grid, so the second use of a row by a neighbouring CTA is an L2 hit.
+// (idx, w) of the cell live in registers (lane j holds neighbour j) and are broadcast with shuffles.
+template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL>
+__global__ void __launch_bounds__(256)
+interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
+                       const Tw* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
+                       Tout* __restrict__ out) {
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t cell = (int64_t)blockIdx.x * warps + warp;
+    if (cell >= n_cells) return;
+    int32_t idx_lo = 0, idx_hi = 0;
+    Tw w_lo = (Tw)0, w_hi = (Tw)0;
+    if (lane < k) { idx_lo = idx[cell * k + lane]; w_lo = w[cell * k + lane]; }
+    if (lane + 32 < k) { idx_hi = idx[cell * k + lane + 32]; w_hi = w[cell * k + lane + 32]; }
+    const int64_t orow = out_row ? (int64_t)out_row[cell] : cell;
+    Tout* o = out + orow * row_len;
+    constexpr int STEP = 32 * V;
+    for (int64_t col0 = 0; col0 < row_len; col0 += (int64_t)STEP * UNROLL) {
+        Tw acc[UNROLL][V];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[u][e] = (Tw)0;
+        // One neighbour at a time on purpose: ncu shows this kernel bound by the L1 data pipe (LDG.128 = 4 wavefronts
+        // at ~2 cycles each), not by latency; batching 8 neighbours' loads per lane (tried) only lowered the L1 hit
+        // rate and cost 25 %.  The UNROLL column vectors of one neighbour are independent loads.
+        for (int j = 0; j < k; ++j) {
+            const int32_t r = __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
+            const Tw wj = __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            const Tin* src = data + (int64_t)r * row_len + col0 + lane * V;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (col0 + u * STEP + lane * V < row_len) {
+                    const Vec<Tin, V> x = ld_stream<Tin, V>(src + u * STEP);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        if (MODE == 0) acc[u][e] = fmaf((float)wj, (float)x.v[e], (float)acc[u][e]);
+                        else acc[u][e] = __dadd_rn((double)acc[u][e], __dmul_rn((double)wj, (double)x.v[e]));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t c = col0 + u * STEP + lane * V;
+            if (c < row_len) {
+                Vec<Tout, V> ov;
+#pragma unroll
+                for (int e = 0; e < V; ++e) ov.v[e] = (Tout)acc[u][e];
+                *reinterpret_cast<Vec<Tout, V>*>(o + c) = ov;
+            }
+        }
+    }
+}
+
 template <typename Tin, typename Tw, typename Tout, int MODE>
 static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, const void* w, int64_t n_cells, int k,
                          const int32_t* out_row, void* out, cudaStream_t stream) {
     if (n_cells == 0 || row_len == 0) return S3_OK;
     constexpr int VFULL = 16 / sizeof(Tin);
+    const int kCellsPerCta = g_cells_per_cta;
     const bool vec_ok = (row_len % VFULL == 0) && (((uintptr_t)data) % 16 == 0) &&
                         (((uintptr_t)out) % (sizeof(Tout) * VFULL) == 0);
     const size_t smem = ((sizeof(int32_t) * kCellsPerCta * k + 15) / 16) * 16 + sizeof(Tw) * kCellsPerCta * k;
-    const int64_t tiles = ceil_div(n_cells, kCellsPerCta);
-    S3_REQUIRE(tiles <= 65535 * (int64_t)65535, "too many cells");
-    // blockIdx.y is limited to 65535: fold larger tile counts by looping launches
-    const int64_t max_y = 65535;
-    for (int64_t t0 = 0; t0 < tiles; t0 += max_y) {
-        const int64_t ty = (tiles - t0) < max_y ? (tiles - t0) : max_y;
-        const int64_t cell_off = t0 * kCellsPerCta;
-        const int64_t cells_here = (n_cells - cell_off) < ty * kCellsPerCta ? (n_cells - cell_off) : ty * kCellsPerCta;
-        const int32_t* idx_p = idx + cell_off * k;
-        const Tw* w_p = reinterpret_cast<const Tw*>(w) + cell_off * k;
-        const int32_t* orow_p = out_row ? out_row + cell_off : nullptr;
-        Tout* out_p = reinterpret_cast<Tout*>(out) + (out_row ? 0 : cell_off * row_len);
-        if (vec_ok) {
-            dim3 grid((unsigned)ceil_div(row_len, (int64_t)kInterpThreads * VFULL), (unsigned)ty);
-            interp_gather_kernel<Tin, Tw, Tout, VFULL, MODE><<<grid, kInterpThreads, smem, stream>>>(
-                reinterpret_cast<const Tin*>(data), row_len, idx_p, w_p, cells_here, k, orow_p, out_p);
-        } else {
-            dim3 grid((unsigned)ceil_div(row_len, (int64_t)kInterpThreads), (unsigned)ty);
-            interp_gather_kernel<Tin, Tw, Tout, 1, MODE><<<grid, kInterpThreads, smem, stream>>>(
-                reinterpret_cast<const Tin*>(data), row_len, idx_p, w_p, cells_here, k, orow_p, out_p);
-        }
+    const Tw* w_p = reinterpret_cast<const Tw*>(w);
+    Tout* out_p = reinterpret_cast<Tout*>(out);
+    if (g_direct_variant == 1 && k <= 64) {
+        const int warps = g_warps_per_cta;
+        const int64_t blocks = ceil_div(n_cells, warps);
+        S3_REQUIRE(blocks < ((int64_t)1 << 31), "too many cells");
+        if (vec_ok && g_unroll == 2)
+            interp_warpcell_kernel<Tin, Tw, Tout, VFULL, MODE, 2><<<(unsigned)blocks, warps * 32, 0, stream>>>(
+                reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p);
+        else if (vec_ok)
+            interp_warpcell_kernel<Tin, Tw, Tout, VFULL, MODE, 1><<<(unsigned)blocks, warps * 32, 0, stream>>>(
+                reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p);
+        else
+            interp_warpcell_kernel<Tin, Tw, Tout, 1, MODE, 2><<<(unsigned)blocks, warps * 32, 0, stream>>>(
+                reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p);
         S3_LAUNCH_CHECK();
         note_launch(1);
+        return S3_OK;
     }
+    const int64_t tiles = ceil_div(n_cells, kCellsPerCta);
+    S3_REQUIRE(tiles < ((int64_t)1 << 31), "too many cells");
+    // blockIdx.x = cell tile (consecutive CTAs work on neighbouring cells), blockIdx.y = column chunk
+    if (vec_ok) {
+        dim3 grid((unsigned)tiles, (unsigned)ceil_div(row_len, (int64_t)kInterpThreads * VFULL));
+        interp_gather_kernel<Tin, Tw, Tout, VFULL, MODE><<<grid, kInterpThreads, smem, stream>>>(
+            reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, kCellsPerCta);
+    } else {
+        dim3 grid((unsigned)tiles, (unsigned)ceil_div(row_len, (int64_t)kInterpThreads));
+        interp_gather_kernel<Tin, Tw, Tout, 1, MODE><<<grid, kInterpThreads, smem, stream>>>(
+            reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, kCellsPerCta);
+    }
+    S3_LAUNCH_CHECK();
+    note_launch(1);
     return S3_OK;
 }
 
 }  // namespace s3
 
 using namespace s3;
+
+extern "C" int s3_set_tuning(int key, int value) {
+    if (key == 0) {
+        S3_REQUIRE(value >= 1 && value <= kMaxCellsPerCta, "s3_set_tuning: cells per CTA must be in [1, %d]", kMaxCellsPerCta);
+        s3::g_cells_per_cta = value;
+        return S3_OK;
+    }
+    if (key == 1) {
+        S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: staging must be 0 (TMA) or 1 (cp.async)");
+        s3::g_staging = value;
+        return S3_OK;
+    }
+    if (key == 3) {
+        S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: direct variant must be 0 or 1");
+        s3::g_direct_variant = value;
+        return S3_OK;
+    }
+    if (key == 4) {
+        S3_REQUIRE(value >= 1 && value <= 8, "s3_set_tuning: warps per CTA must be 1..8");
+        s3::g_warps_per_cta = value;
+        return S3_OK;
+    }
+    if (key == 5) {
+        S3_REQUIRE(value == 1 || value == 2, "s3_set_tuning: unroll must be 1 or 2");
+        s3::g_unroll = value;
+        return S3_OK;
+    }
+    if (key == 2) {
+        S3_REQUIRE(value >= 8 && value <= 200, "s3_set_tuning: staging budget must be 8..200 KB");
+        s3::g_stage_budget_kb = value;
+        return S3_OK;
+    }
+    s3::set_error("s3_set_tuning: unknown key %d", key);
+    return S3_ERR_INVALID;
+}
 
 extern "C" int s3_interp_gather(const void* d_data, int data_dtype, int64_t n_src, int64_t row_len,
                                 const int32_t* d_idx, const void* d_w, int64_t n_cells, int k,

@@ -16,6 +16,8 @@ namespace s3 {
 constexpr int kTileCells = 32;
 constexpr int kTileThreads = 256;
 constexpr int kTileMaxRefs = 2048;  // kTileCells * k rounded up to a power of two must fit
+int g_staging = 0;                  // 0 = TMA bulk copies, 1 = cp.async (s3_set_tuning key 1)
+int g_stage_budget_kb = 56;         // shared memory per CTA for staged rows (s3_set_tuning key 2)
 
 // Tile preprocessing (once per KNN cache): unique source rows of the tile + local index of every reference.
 __global__ void __launch_bounds__(kTileThreads)
@@ -80,7 +82,14 @@ tile_build_kernel(const int32_t* __restrict__ idx, int64_t n_cells, int k, int r
     }
 }
 
-template <int W>   // W = staged columns per row (floats), multiple of 128
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <int W, int STAGING>   // W = staged columns per row (floats), multiple of 128; STAGING 0 = TMA bulk, 1 = cp.async
 __global__ void __launch_bounds__(kTileThreads)
 interp_staged_kernel(const float* __restrict__ data, int64_t row_len, const int32_t* __restrict__ tile_rows,
                      const int32_t* __restrict__ tile_nrows, const uint16_t* __restrict__ tile_lidx,
@@ -104,18 +113,32 @@ interp_staged_kernel(const float* __restrict__ data, int64_t row_len, const int3
     const uint32_t row_bytes = (uint32_t)wcur * 4u;
     const int32_t* rows = tile_rows + tile * cap;
 
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, (uint32_t)nstage * row_bytes + (uint32_t)cap * 6u);
-        tma_load_1d(s_w, w + tile * cap, (uint32_t)cap * 4u, &bar);
-        tma_load_1d(s_lidx, tile_lidx + tile * cap, (uint32_t)cap * 2u, &bar);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        for (int r = threadIdx.x; r < nstage; r += 32)
+    if (STAGING == 0) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)nstage * row_bytes + (uint32_t)cap * 6u);
+            tma_load_1d(s_w, w + tile * cap, (uint32_t)cap * 4u, &bar);
+            tma_load_1d(s_lidx, tile_lidx + tile * cap, (uint32_t)cap * 2u, &bar);
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < nstage; r += kTileThreads)
             tma_load_1d(s_rows + (size_t)r * W, data + (int64_t)rows[r] * row_len + col0, row_bytes, &bar);
+        mbar_wait(&bar, 0);
+    } else {
+        // 16-byte cp.async pieces issued by all threads; a warp covers 512 contiguous bytes of one row
+        const int ppr = wcur >> 2;                       // 16-byte pieces per row
+        const int total = nstage * ppr;
+        for (int p = threadIdx.x; p < total; p += kTileThreads) {
+            const int r = p / ppr, c4 = p - r * ppr;
+            cp_async_16(s_rows + (size_t)r * W + c4 * 4, data + (int64_t)rows[r] * row_len + col0 + c4 * 4);
+        }
+        for (int i = threadIdx.x; i < cap; i += kTileThreads) {
+            s_w[i] = w[tile * cap + i];
+            s_lidx[i] = tile_lidx[tile * cap + i];
+        }
+        cp_async_commit_wait_all();
+        __syncthreads();
     }
-    mbar_wait(&bar, 0);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int S = W / 128;
@@ -192,7 +215,7 @@ extern "C" int s3_interp_staged(const float* d_data, int64_t n_src, int64_t row_
     if (n_cells == 0 || row_len == 0) return S3_OK;
     const int cap = kTileCells * k;
     const size_t table_bytes = (size_t)cap * 6;
-    const size_t budget = 200 * 1024;
+    const size_t budget = (size_t)g_stage_budget_kb * 1024;
     int r_smem = max_rows < 1 ? 1 : max_rows;
     const size_t max_fit = (budget - table_bytes) / ((size_t)chunk_cols * 4);
     if ((size_t)r_smem > max_fit) r_smem = (int)max_fit;
@@ -202,15 +225,19 @@ extern "C" int s3_interp_staged(const float* d_data, int64_t n_src, int64_t row_
     const int64_t blocks = tiles * n_chunks;
     S3_REQUIRE(blocks < ((int64_t)1 << 31), "s3_interp_staged: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
-    if (chunk_cols == 128) {
-        S3_CUDA(cudaFuncSetAttribute(interp_staged_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        interp_staged_kernel<128><<<(unsigned)blocks, kTileThreads, smem, st>>>(
-            d_data, row_len, d_tile_rows, d_tile_nrows, d_tile_lidx, d_w, n_cells, k, n_chunks, r_smem, d_out_row, d_out);
-    } else {
-        S3_CUDA(cudaFuncSetAttribute(interp_staged_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        interp_staged_kernel<256><<<(unsigned)blocks, kTileThreads, smem, st>>>(
-            d_data, row_len, d_tile_rows, d_tile_nrows, d_tile_lidx, d_w, n_cells, k, n_chunks, r_smem, d_out_row, d_out);
-    }
+#define S3_LAUNCH_STAGED(WW, SS)                                                                                  \
+    do {                                                                                                         \
+        S3_CUDA(cudaFuncSetAttribute(interp_staged_kernel<WW, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     (int)smem));                                                                \
+        interp_staged_kernel<WW, SS><<<(unsigned)blocks, kTileThreads, smem, st>>>(                               \
+            d_data, row_len, d_tile_rows, d_tile_nrows, d_tile_lidx, d_w, n_cells, k, n_chunks, r_smem, d_out_row, \
+            d_out);                                                                                              \
+    } while (0)
+    if (chunk_cols == 128 && g_staging == 0) S3_LAUNCH_STAGED(128, 0);
+    else if (chunk_cols == 128) S3_LAUNCH_STAGED(128, 1);
+    else if (g_staging == 0) S3_LAUNCH_STAGED(256, 0);
+    else S3_LAUNCH_STAGED(256, 1);
+#undef S3_LAUNCH_STAGED
     S3_LAUNCH_CHECK();
     note_launch(1);
     return S3_OK;

@@ -57,9 +57,16 @@ class KnnTables:
         self.out_row = perm.contiguous()
         self.n = q.size(0)
         self.k = k
-        self.tiles = StagedTiles(self.idx_sorted, self.w32_sorted) if 32 * k <= 2048 else None
-        self.mode = "staged"          # "staged" (TMA-staged tiles, fp32) or "direct"
+        self._tiles = None
+        self.mode = "direct"          # "direct" (warp per cell, default) or "staged" (TMA-staged tiles, experimental)
         self.chunk_cols = 256
+
+    @property
+    def tiles(self):
+        """Tile structures of the staged kernel, built on first use."""
+        if self._tiles is None and 32 * self.k <= 2048:
+            self._tiles = StagedTiles(self.idx_sorted, self.w32_sorted)
+        return self._tiles
 
     def interpolate(self, data: pt.Tensor, out_dtype, out: pt.Tensor = None) -> pt.Tensor:
         if out is None:
@@ -76,8 +83,7 @@ class KnnTables:
         import torch.distributed as dist
         for t in (self.idx_sorted, self.w32_sorted, self.w64_sorted, self.out_row):
             dist.broadcast(t, src=src)
-        if self.tiles is not None:
-            self.tiles = StagedTiles(self.idx_sorted, self.w32_sorted)
+        self._tiles = None
         return self
 
 
