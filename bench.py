@@ -198,15 +198,11 @@ def run_ours(args):
         t_grid_wall = time.time() - t0
         grid_info = sc.mesh_info
         centers = sc.centers.to(dev)
-        nc = pt.tensor([centers.size(0)], device=dev)
     else:
-        sc, centers, nc = None, None, pt.zeros(1, dtype=pt.int64, device=dev)
-    if world > 1:
-        dist.broadcast(nc, 0)
-        if rank != 0:
-            centers = pt.empty((int(nc.item()), 2), dtype=pt.float64, device=dev)
-        dist.broadcast(centers, 0)
-    n_cells = int(nc.item())
+        sc, centers = None, None
+    from sparsespatialsampling_b200.parallel import broadcast_grid
+    centers = broadcast_grid(centers, 2, dev, src=0)
+    n_cells = int(centers.size(0))
 
     t0 = time.time()
     index = KnnIndex(xd)

@@ -80,9 +80,8 @@ class KnnTables:
 
     def broadcast_(self, src: int = 0):
         """Share the tables of rank ``src`` with all ranks (NCCL over NVLink; one-off before the export loop)."""
-        import torch.distributed as dist
-        for t in (self.idx_sorted, self.w32_sorted, self.w64_sorted, self.out_row):
-            dist.broadcast(t, src=src)
+        from .parallel import broadcast_tensors
+        broadcast_tensors([self.idx_sorted, self.w32_sorted, self.w64_sorted, self.out_row, self.idx, self.w64], src)
         self._tiles = None
         return self
 

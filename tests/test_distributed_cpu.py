@@ -1,0 +1,54 @@
+"""
+world_size-2 gloo test of the N>1 path (host logic only, no GPU): rank 0 owns the KNN tables and broadcasts them,
+every rank interpolates its own snapshot window, the concatenation equals the single-process result.
+"""
+import os
+import socket
+
+import numpy as np
+import torch as pt
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import s3_oracle as orc
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparsespatialsampling_b200.parallel import snapshot_window, broadcast_tensors, broadcast_grid
+    rng = np.random.default_rng(0)                     # same data on every rank
+    N, Nc, k, T = 400, 150, 8, 11
+    data = rng.standard_normal((N, 2, T)).astype(np.float32)
+    if rank == 0:
+        idx = pt.from_numpy(rng.integers(0, N, (Nc, k)))
+        w = pt.from_numpy(rng.random((Nc, k)))
+        centers = pt.from_numpy(rng.random((Nc, 2)))
+    else:
+        idx, w, centers = pt.zeros((Nc, k), dtype=pt.int64), pt.zeros((Nc, k), dtype=pt.float64), None
+    centers = broadcast_grid(centers, 2, "cpu", src=0)
+    broadcast_tensors([idx, w], src=0)
+    t0, t1 = snapshot_window(T, world, rank)
+    out = orc.interpolate(w.numpy(), idx.numpy(), data[:, :, t0:t1])
+    np.save(os.path.join(tmp, f"part{rank}.npy"), out)
+    np.save(os.path.join(tmp, f"centers{rank}.npy"), centers.numpy())
+    if rank == 0:
+        np.save(os.path.join(tmp, "full.npy"), orc.interpolate(w.numpy(), idx.numpy(), data))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_snapshot_sharded_interpolation_world_size_2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"part{r}.npy") for r in range(world)]
+    full = np.load(tmp_path / "full.npy")
+    assert np.array_equal(np.concatenate(parts, axis=2), full)
+    assert np.array_equal(np.load(tmp_path / "centers0.npy"), np.load(tmp_path / "centers1.npy"))
