@@ -222,6 +222,7 @@ def run_ours(args):
     from sparsespatialsampling_b200.interpolate import interp_gather
 
     tables.mode, tables.chunk_cols = args.kernel, args.chunk_cols
+    tables.stage_rows, tables.n_ctas, tables.gather4 = args.stage_rows, args.ctas, bool(args.gather4)
     if args.staging >= 0:
         _lib.check(_lib.load().s3_set_tuning(1, args.staging))
     if args.stage_kb:
@@ -230,6 +231,8 @@ def run_ours(args):
         _lib.check(_lib.load().s3_set_tuning(3, args.variant))
     if args.warps:
         _lib.check(_lib.load().s3_set_tuning(4, args.warps))
+    if args.prefetch:
+        _lib.check(_lib.load().s3_set_tuning(6, args.prefetch))
     if args.unroll:
         _lib.check(_lib.load().s3_set_tuning(5, args.unroll))
     if args.cells_per_cta:
@@ -345,9 +348,10 @@ def run_ours(args):
                    "l2_policy": "inputs larger than L2 (1.2 GB of snapshot rows per step vs 126 MB L2)",
                    "sharding": "snapshot window per rank; grid + KNN tables broadcast once over NCCL",
                    "kernel": args.kernel, "chunk_cols": args.chunk_cols,
-                   "unique_rows_per_tile_sum": tables.tiles.total_rows if tables.tiles is not None else None},
+                   "unique_rows_per_tile_sum": tables.tiles.total_rows if args.kernel != "direct" else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "interp_staged_kernel" if args.kernel == "staged" else "interp_gather_kernel",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": {"staged": "interp_staged_kernel", "pipe": "interp_pipe_kernel",
+                                "direct": "interp_warpcell_kernel"}[args.kernel],
                      "algorithmic_bytes_per_step": b_algo, "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -374,13 +378,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="s3b200", choices=["s3b200", "reference"])
-    ap.add_argument("--kernel", default="direct", choices=["staged", "direct"], help="interpolation kernel variant")
+    ap.add_argument("--kernel", default="direct", choices=["staged", "direct", "pipe"], help="interpolation kernel variant")
     ap.add_argument("--cells-per-cta", type=int, default=0, help="direct kernel: cells per CTA (0 = library default)")
     ap.add_argument("--staging", type=int, default=-1, help="staged kernel: 0 = TMA bulk copies, 1 = cp.async")
     ap.add_argument("--stage-kb", type=int, default=0, help="staged kernel: shared-memory budget per CTA in KB")
     ap.add_argument("--variant", type=int, default=-1, help="direct kernel: 0 = CTA walks cells, 1 = warp per cell")
     ap.add_argument("--warps", type=int, default=0, help="warp-per-cell kernel: warps (= cells) per CTA")
     ap.add_argument("--unroll", type=int, default=0, help="warp-per-cell kernel: column vectors per lane and step")
+    ap.add_argument("--stage-rows", type=int, default=0, help="pipelined kernel: rows per shared-memory stage")
+    ap.add_argument("--ctas", type=int, default=0, help="pipelined kernel: persistent CTAs (0 = one per SM)")
+    ap.add_argument("--prefetch", type=int, default=0, help="pipelined kernel: L2 prefetch distance in work items")
+    ap.add_argument("--gather4", type=int, default=1, help="pipelined kernel: 1 = TMA gather4, 0 = 1-D bulk copies")
     ap.add_argument("--chunk-cols", type=int, default=256, choices=[128, 256], help="columns staged per CTA")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -151,6 +151,16 @@ int s3_interp_staged(const float* d_data, int64_t n_src, int64_t row_len, const 
                      int64_t n_cells, int k, int max_rows, int chunk_cols, const int32_t* d_out_row,
                      float* d_out, void* stream);
 
+/* Pipelined persistent variant of s3_interp_staged (same tile structures): one CTA per SM, a producer warp
+ * feeds a ring of shared-memory stages with TMA bulk copies while 8 consumer warps interpolate from the
+ * previous stages. stage_rows = rows held per stage (0 = max_rows; further rows of a tile are read
+ * directly); n_ctas = grid size (0 = number of SMs); use_gather4 != 0: fetch the rows four at a time with
+ * the Blackwell TMA gather (cp.async.bulk.tensor.2d...tile::gather4) instead of one bulk copy per row.   */
+int s3_interp_pipelined(const float* d_data, int64_t n_src, int64_t row_len, const int32_t* d_tile_rows,
+                        const int32_t* d_tile_nrows, const uint16_t* d_tile_lidx, const float* d_w,
+                        int64_t n_cells, int k, int max_rows, int chunk_cols, int stage_rows, int n_ctas,
+                        int use_gather4, const int32_t* d_out_row, float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "s3_interp_tiles_build": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "s3_interp_staged": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "s3_interp_pipelined": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -17,6 +17,7 @@ namespace s3 {
 
 extern int g_staging;
 extern int g_stage_budget_kb;
+extern int g_pipe_prefetch;
 constexpr int kInterpThreads = 128;
 constexpr int kMaxCellsPerCta = 32;
 static int g_cells_per_cta = 4;
@@ -242,6 +243,11 @@ extern "C" int s3_set_tuning(int key, int value) {
     if (key == 4) {
         S3_REQUIRE(value >= 1 && value <= 8, "s3_set_tuning: warps per CTA must be 1..8");
         s3::g_warps_per_cta = value;
+        return S3_OK;
+    }
+    if (key == 6) {
+        S3_REQUIRE(value >= 0 && value <= 64, "s3_set_tuning: prefetch distance must be 0..64");
+        s3::g_pipe_prefetch = value;
         return S3_OK;
     }
     if (key == 5) {

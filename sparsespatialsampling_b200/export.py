@@ -60,6 +60,9 @@ class KnnTables:
         self._tiles = None
         self.mode = "direct"          # "direct" (warp per cell, default) or "staged" (TMA-staged tiles, experimental)
         self.chunk_cols = 256
+        self.stage_rows = 0
+        self.n_ctas = 0
+        self.gather4 = True
 
     @property
     def tiles(self):
@@ -72,9 +75,11 @@ class KnnTables:
         if out is None:
             out = pt.empty((self.n,) + tuple(data.shape[1:]), dtype=out_dtype, device=data.device)
         row_len = data.numel() // max(data.size(0), 1)
-        if (self.mode == "staged" and self.tiles is not None and out_dtype == pt.float32 and
+        if (self.mode in ("staged", "pipe") and self.tiles is not None and out_dtype == pt.float32 and
                 data.dtype == pt.float32 and row_len % 4 == 0):
-            return self.tiles.interpolate(data, out=out, out_row=self.out_row, chunk_cols=self.chunk_cols)
+            return self.tiles.interpolate(data, out=out, out_row=self.out_row, chunk_cols=self.chunk_cols,
+                                          pipelined=self.mode == "pipe", stage_rows=self.stage_rows,
+                                          n_ctas=self.n_ctas, gather4=self.gather4)
         w = self.w32_sorted if out_dtype == pt.float32 else self.w64_sorted
         return interp_gather(data, self.idx_sorted, w, out=out, out_row=self.out_row, out_dtype=out_dtype)
 

@@ -96,7 +96,8 @@ class StagedTiles:
         self.total_rows = int(self.nrows.sum().item()) if self.n_tiles else 0
 
     def interpolate(self, data: pt.Tensor, out: pt.Tensor = None, out_row: pt.Tensor = None,
-                    chunk_cols: int = 256) -> pt.Tensor:
+                    chunk_cols: int = 256, pipelined: bool = False, stage_rows: int = 0, n_ctas: int = 0,
+                    gather4: bool = True) -> pt.Tensor:
         lib = _lib.load()
         assert data.is_cuda and data.dtype == pt.float32
         data = data.contiguous()
@@ -104,8 +105,17 @@ class StagedTiles:
         row_len = data.numel() // max(n_src, 1)
         if out is None:
             out = pt.empty((self.n_cells,) + tuple(data.shape[1:]), dtype=pt.float32, device=data.device)
+        if pipelined:
+            with pt.cuda.device(data.device):
+                _lib.check(lib.s3_interp_pipelined(_lib.ptr(data), n_src, row_len, _lib.ptr(self.rows),
+                                                   _lib.ptr(self.nrows), _lib.ptr(self.lidx), _lib.ptr(self.w),
+                                                   self.n_cells, self.k, self.max_rows, int(chunk_cols),
+                                                   int(stage_rows), int(n_ctas), int(gather4), _lib.ptr(out_row), _lib.ptr(out),
+                                                   _lib.stream_ptr()))
+            return out
         with pt.cuda.device(data.device):
             _lib.check(lib.s3_interp_staged(_lib.ptr(data), n_src, row_len, _lib.ptr(self.rows), _lib.ptr(self.nrows),
                                             _lib.ptr(self.lidx), _lib.ptr(self.w), self.n_cells, self.k, self.max_rows,
                                             int(chunk_cols), _lib.ptr(out_row), _lib.ptr(out), _lib.stream_ptr()))
         return out
+

@@ -96,6 +96,11 @@ def test_staged_kernel_equals_direct_kernel(cuda, N, Nc, k, D, T, chunk):
     tiles = StagedTiles(i, wt)
     staged = tiles.interpolate(d, chunk_cols=chunk)
     assert pt.equal(staged, direct)
+    for stage_rows, n_ctas, g4 in [(0, 0, False), (24, 3, False), (7, 148, False), (0, 0, True), (24, 5, True),
+                                   (8, 148, True)]:     # pipelined persistent variant, incl. row overflow
+        piped = tiles.interpolate(d, chunk_cols=chunk, pipelined=True, stage_rows=stage_rows, n_ctas=n_ctas,
+                                  gather4=g4)
+        assert pt.equal(piped, direct), (stage_rows, n_ctas, g4)
     ref = orc.interpolate(w, idx.astype(np.int64), data)
     scale = np.abs(data[idx]).max(axis=1)
     assert (np.abs(staged.cpu().numpy() - ref) <= RTOL_F32 * np.maximum(scale, 1e-30)).all()
