@@ -1,0 +1,135 @@
+"""
+GPU tests of the surface-defined geometry plugins (GeometrySTL3D, GeometryCoordinates2D): the reference's own unit
+tests (sparseSpatialSampling/tests/test_geometry_STL.py:31-63, test_coordinates_2d_geometry.py:37-71, restated with a
+generated unit-cube STL), device-vs-oracle parity on dense point sets, and analytic sanity checks.
+Beyond the reference's unit tests the parity of these two masks with VTK / shapely is unpinned.
+"""
+import numpy as np
+import pytest
+import torch as pt
+
+from oracle import s3_oracle as orc
+from tests.stl_util import write_binary_stl, cube_triangles, icosphere_triangles
+from tests.test_geometry_gpu import DummyCells
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def cube_stl(tmp_path):
+    p = tmp_path / "cube.stl"
+    write_binary_stl(p, cube_triangles())
+    return str(p)
+
+
+@pytest.mark.parametrize("keep_inside,expected", [(False, (False, True, False)), (True, (True, False, False))])
+def test_stl_reference_unit_triples(cuda, cube_stl, keep_inside, expected):
+    from sparsespatialsampling_b200.geometry import GeometrySTL3D
+    g = GeometrySTL3D("cube", keep_inside=keep_inside, path_stl_file=cube_stl)
+    c = DummyCells()
+    # inside cell = the cube's own corners: on-surface points count as inside
+    got = (g.check_cell(c.cell_outside_3D), g.check_cell(c.cell_inside_3D), g.check_cell(c.cell_partially_3D))
+    assert got == expected
+    assert g.type == "STL" and g.main_width == 1.0 and pt.allclose(g.center, pt.full((3,), 0.5, dtype=pt.float64))
+
+
+def test_stl_pre_check_cell(cuda, cube_stl):
+    from sparsespatialsampling_b200.geometry import GeometrySTL3D
+    g = GeometrySTL3D("cube", keep_inside=False, path_stl_file=cube_stl)
+    c = DummyCells()
+    assert g.pre_check_cell(c.cell_inside_3D) is True
+    assert g.pre_check_cell(c.cell_outside_3D) is False
+
+
+def test_stl_rejects_open_surfaces_and_decimation(cuda, tmp_path, cube_stl):
+    from sparsespatialsampling_b200.geometry import GeometrySTL3D
+    p = tmp_path / "open.stl"
+    write_binary_stl(p, cube_triangles()[:-2])            # one face missing
+    with pytest.raises(RuntimeError):
+        GeometrySTL3D("open", False, str(p))
+    with pytest.raises(NotImplementedError):
+        GeometrySTL3D("cube", False, cube_stl, reduce_by=0.5)
+
+
+def test_stl_sphere_matches_oracle_and_analytic(cuda, tmp_path):
+    from sparsespatialsampling_b200.geometry import GeometrySTL3D
+    from sparsespatialsampling_b200.geometry.device import nodes_inside
+    p = tmp_path / "sphere.stl"
+    write_binary_stl(p, icosphere_triangles(3, radius=0.7, center=(0.1, -0.2, 0.3)))
+    g = GeometrySTL3D("sphere", False, str(p))
+    assert g._triangles.shape[0] == 1280
+    rng = np.random.default_rng(0)
+    pts = rng.random((20000, 3)) * 2.0 - 1.0 + np.array([0.1, -0.2, 0.3])
+    got = nodes_inside(g, pt.from_numpy(pts)).numpy()
+    assert np.array_equal(got, orc.points_inside(g, pts))
+    r = np.linalg.norm(pts - np.array([0.1, -0.2, 0.3]), axis=1)
+    clear = np.abs(r - 0.7) > 0.03                       # away from the faceted surface / tolerance band
+    assert np.array_equal(got[clear], (r < 0.7)[clear])
+
+
+@pytest.mark.parametrize("keep_inside,expected", [(False, (False, True, False)), (True, (True, False, False))])
+def test_polygon_reference_unit_triples(cuda, keep_inside, expected):
+    from sparsespatialsampling_b200.geometry import GeometryCoordinates2D
+    g = GeometryCoordinates2D("square", keep_inside=keep_inside,
+                              coordinates=[(-1, -1), (-1, 1.25), (1.25, 1.25), (1.25, -1)])
+    c = DummyCells()
+    got = (g.check_cell(c.cell_outside_2D), g.check_cell(c.cell_inside_2D), g.check_cell(c.cell_partially_2D))
+    assert got == expected
+    assert g.type == "coord_2D" and g.main_width == 2.25
+
+
+def test_polygon_pre_check_and_boundary(cuda):
+    from sparsespatialsampling_b200.geometry import GeometryCoordinates2D
+    from sparsespatialsampling_b200.geometry.device import nodes_inside
+    g = GeometryCoordinates2D("square", False, [(-1, -1), (-1, 1.25), (1.25, 1.25), (1.25, -1)])
+    assert g.pre_check_cell(pt.tensor([[0.0, 0.0]])) is True
+    assert g.pre_check_cell(pt.tensor([[5.0, 5.0]])) is False
+    # shapely's within() is the strict interior: boundary points are outside
+    edge = pt.tensor([[-1.0, 0.0], [1.25, 1.25], [0.0, 1.25], [0.0, 0.0]], dtype=pt.float64)
+    assert nodes_inside(g, edge).tolist() == [False, False, False, True]
+
+
+def test_polygon_star_matches_oracle(cuda):
+    from sparsespatialsampling_b200.geometry import GeometryCoordinates2D
+    from sparsespatialsampling_b200.geometry.device import nodes_inside
+    ang = np.linspace(0, 2 * np.pi, 21)[:-1]
+    rad = np.where(np.arange(20) % 2 == 0, 1.0, 0.45)
+    star = np.stack([rad * np.cos(ang), rad * np.sin(ang)], 1)
+    g = GeometryCoordinates2D("star", False, star.tolist() + [star[0].tolist()])      # closed ring input
+    assert g._vertices.shape[0] == 20
+    pts = np.random.default_rng(1).random((30000, 2)) * 2.4 - 1.2
+    got = nodes_inside(g, pt.from_numpy(pts)).numpy()
+    assert np.array_equal(got, orc.points_inside(g, pts))
+    assert 0.2 < got.mean() < 0.4
+
+
+def test_grid_generation_with_stl_and_polygon_matches_oracle(cuda, tmp_path):
+    import synth
+    import sparsespatialsampling_b200.geometry as geo
+    from sparsespatialsampling_b200.s_cube import SamplingTree
+    # 3-D: STL sphere body inside a box domain
+    p = tmp_path / "ball.stl"
+    write_binary_stl(p, icosphere_triangles(2, radius=0.3, center=(0.8, 1.0, 0.16)))
+    x = synth.cylinder3d_cloud(5000, seed=4)
+    m = synth.wake_metric(x, xc=0.8, yc=1.0)
+    mk = lambda: [geo.CubeGeometry("domain", True, synth.CYL3D["lower"], synth.CYL3D["upper"]),
+                  geo.GeometrySTL3D("ball", False, str(p), refine=True)]
+    kw = dict(uniform_level=3, min_metric=0.4, n_cells_iter_start=10)
+    tree = SamplingTree(x, m, mk(), **kw, sdm_order=1)
+    tree.refine()
+    o = orc.OracleTree(x.numpy(), m.numpy(), mk(), **kw, sdm_order=1).refine()
+    assert list(tree._leaf_cells) == o.leaf_order
+    assert np.array_equal(tree.all_centers.numpy(), o.all_centers)
+    # 2-D: polygon body (the OAT15-style set-up of the reference's example uses GeometryCoordinates2D)
+    x2 = synth.airfoil2d_cloud(5000, seed=6)
+    m2 = synth.wake_metric(x2, xc=1.0, yc=0.0)
+    wedge = [(0.0, 0.0), (1.0, 0.06), (1.0, -0.06)]
+    mk2 = lambda: [geo.CubeGeometry("domain", True, synth.AIRFOIL2D["lower"], synth.AIRFOIL2D["upper"]),
+                   geo.GeometryCoordinates2D("airfoil", False, wedge, refine=True, min_refinement_level=7)]
+    kw2 = dict(uniform_level=4, n_cells=1200, n_cells_iter_start=40)
+    t2 = SamplingTree(x2, m2, mk2(), **kw2, sdm_order=1)
+    t2.refine()
+    o2 = orc.OracleTree(x2.numpy(), m2.numpy(), mk2(), **kw2, sdm_order=1).refine()
+    assert list(t2._leaf_cells) == o2.leaf_order
+    assert np.array_equal(t2.all_centers.numpy(), o2.all_centers)
+    assert np.array_equal(t2.all_levels.numpy(), o2.all_levels)

@@ -85,3 +85,24 @@ def test_snapshot_windows_partition_the_time_axis():
         assert all(a[1] == b[0] for a, b in zip(wins, wins[1:]))
         sizes = [b - a for a, b in wins]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_surface_geometry_oracle_meets_reference_unit_tests(tmp_path):
+    # the reference's own expectations for GeometrySTL3D / GeometryCoordinates2D (tests/test_geometry_STL.py:31-63,
+    # tests/test_coordinates_2d_geometry.py:37-71), evaluated with the CPU oracle of the documented restatement
+    import sparsespatialsampling_b200.geometry as g
+    from tests.stl_util import write_binary_stl, cube_triangles
+    from tests.test_geometry_gpu import DummyCells
+    p = tmp_path / "cube.stl"
+    write_binary_stl(p, cube_triangles())
+    c = DummyCells()
+    for keep_inside, expected in [(False, [False, True, False]), (True, [True, False, False])]:
+        stl = g.GeometrySTL3D("cube", keep_inside, str(p))
+        got = [orc.check_cell(stl, getattr(c, n).double().numpy())
+               for n in ("cell_outside_3D", "cell_inside_3D", "cell_partially_3D")]
+        assert got == expected
+        poly = g.GeometryCoordinates2D("square", keep_inside, [(-1, -1), (-1, 1.25), (1.25, 1.25), (1.25, -1)])
+        got = [orc.check_cell(poly, getattr(c, n).double().numpy())
+               for n in ("cell_outside_2D", "cell_inside_2D", "cell_partially_2D")]
+        assert got == expected
+    assert g.GeometrySTL3D("cube", False, str(p)).device_params()[2] == 12
