@@ -259,12 +259,13 @@ class OracleTree:
     """
     CPU restatement of SamplingTree (s_cube.py:86-902, 1538-1584) on flat Python lists; control flow and the set
     operations that define the cell numbering follow the reference line by line.
-    ``max_delta_level`` is not restated.
+    ``max_delta_level`` (s_cube.py:447-506) is restated geometrically: the neighbour of a cell in a direction is the
+    leaf covering the adjacent same-level lattice position; the reference reaches it through neighbour pointers.
     """
 
     def __init__(self, vertices, target, geometries, n_cells=None, uniform_level=5, min_metric=0.75,
                  n_cells_iter_start=None, n_cells_iter_end=None, relTol=1e-3, reach_at_least=0.75, pre_select=False,
-                 sdm_order=1):
+                 sdm_order=1, max_delta_level=False):
         self.X = np.ascontiguousarray(vertices, dtype=np.float64)
         self.y = np.ascontiguousarray(target, dtype=np.float64)
         self.geometries = geometries
@@ -280,6 +281,14 @@ class OracleTree:
         self.cpi, self.cpi_last = self.cpi_start, 1e9
         self.relTol, self.reach_at_least, self.pre_select, self.sdm_order = relTol, reach_at_least, pre_select, sdm_order
         self.metric_log, self.n_cells_log = [], []
+        self.max_delta_level = max_delta_level
+        self.lattice, self.lookup = [], {}
+        plane = [(-1, 0), (-1, 1), (0, 1), (1, 1), (1, 0), (1, -1), (0, -1), (-1, -1)]      # NB order, s_cube.py:22-26
+        if self.d == 2:
+            self.nb_dirs = plane
+        else:
+            self.nb_dirs = ([p + (0,) for p in plane] + [p + (-1,) for p in plane + [(0, 0)]] +
+                            [p + (1,) for p in plane + [(0, 0)]])
         self.center, self.level, self.gain, self.metric, self.invalid = [], [], [], [], []
         self.leaf = set()
         self.iterations = 0
@@ -298,6 +307,7 @@ class OracleTree:
         self.gain0 = float(g0)
         self.center.append(c[0].copy()); self.level.append(0); self.gain.append(self.gain0)
         self.metric.append(float(m[0])); self.invalid.append(False)
+        self.lattice.append((0,) * self.d); self.lookup[(0,) + (0,) * self.d] = 0
         self.leaf.add(0)
         self.target_norm = float(np.linalg.norm(self.y))
 
@@ -312,6 +322,9 @@ class OracleTree:
             for j in range(self.nch):
                 self.center.append(ch[j]); self.level.append(self.level[i] + 1)
                 self.gain.append(0.0); self.metric.append(0.0); self.invalid.append(False)
+                lat = tuple(2 * self.lattice[i][a] + (1 if self.dirs[j][a] > 0 else 0) for a in range(self.d))
+                self.lattice.append(lat)
+                self.lookup[(self.level[i] + 1,) + lat] = len(self.center) - 1
             all_children.update(list(range(new_index, new_index + self.nch)))
             all_parents.add(i)
             new_index += self.nch
@@ -320,6 +333,33 @@ class OracleTree:
         new = list(range(first, new_index))
         self._update_gain(new)
         return new
+
+    def _check_nb(self, c):
+        lv, pos, out = self.level[c], self.lattice[c], []
+        for dv in self.nb_dirs:
+            q = tuple(pos[a] + dv[a] for a in range(self.d))
+            if min(q) < 0 or max(q) >= (1 << lv):
+                continue
+            for up in range(lv + 1):
+                n = self.lookup.get((lv - up,) + tuple(v >> up for v in q))
+                if n is None:
+                    continue
+                if up > 0 and n in self.leaf:
+                    out.append(n)
+                break
+        return out
+
+    def _check_constraint(self, viol):
+        go = True if viol else False
+        while go:
+            tmp = set()
+            for c in viol:
+                tmp.update(self._check_nb(c))
+            if not tmp or tmp.issubset(viol):
+                go = False
+            else:
+                viol.update(tmp)
+        return viol
 
     def _update_gain(self, cells):
         if not cells:
@@ -403,6 +443,8 @@ class OracleTree:
             to_refine = set()
             for i in srt:
                 to_refine.add(i)
+                if self.max_delta_level:
+                    to_refine.update(self._check_constraint(set(self._check_nb(i))))
             self._remove_invalid_cells({c for c in self._refine_cells(to_refine)})
             if self.n_cells_max is None:
                 self._captured()
@@ -421,10 +463,17 @@ class OracleTree:
             lo = min(self.level[c] for c in cells)
             hi = max(self.level[c] for c in cells) if g.min_refinement_level is None else g.min_refinement_level
             while hi > lo:
-                to_refine = set()
+                to_refine, checked = set(), set()
                 for i in cells:
+                    if i in checked:
+                        continue
                     if self.level[i] < hi:
                         to_refine.add(i)
+                    if self.max_delta_level:
+                        more = set(self._check_nb(i))
+                        more.update(self._check_constraint(more))
+                        to_refine.update(more)
+                        checked.update(more)
                 idx_new = {c for c in self._refine_cells(to_refine)}
                 self._remove_invalid_cells(idx_new, geometry_no=gi)
                 found = self._remove_invalid_cells({i for i in idx_new if not self.invalid[i]}, True, gi)

@@ -94,9 +94,16 @@ class SamplingTree(object):
         self._nch = 2 ** self._n_dimensions
         self._sdm_order = probe_sum_order_8() if sdm_order is None else int(sdm_order)
 
-        if max_delta_level:
-            raise NotImplementedError("max_delta_level=True (neighbour-level constraint, s_cube.py:447-506) is not "
-                                      "available in the device engine yet.")
+        # neighbour directions in the reference's NB order (s_cube.py:22-26): same plane w, nw, n, ne, e, se, s, sw;
+        # 3-D adds the lower plane (z-1: same eight + centre) and then the upper plane (z+1)
+        plane = [(-1, 0), (-1, 1), (0, 1), (1, 1), (1, 0), (1, -1), (0, -1), (-1, -1)]
+        if self._n_dimensions == 2:
+            self._nb_dirs = [np.array(p, dtype=np.int64) for p in plane]
+        else:
+            self._nb_dirs = ([np.array(p + (0,), dtype=np.int64) for p in plane] +
+                             [np.array(p + (-1,), dtype=np.int64) for p in plane + [(0, 0)]] +
+                             [np.array(p + (1,), dtype=np.int64) for p in plane + [(0, 0)]])
+        self._cell_lookup = {} if max_delta_level else None       # (level, lattice coords) -> cell index
 
         # KNN index over the original grid with the metric as regression target (s_cube.py:161-163)
         t0 = time()
@@ -126,6 +133,7 @@ class SamplingTree(object):
         self._center = self._level = self._lattice = self._gain = self._metric_d = self._flags = None
         self._levels_h = np.zeros(0, dtype=np.int32)
         self._invalid_h = np.zeros(0, dtype=bool)
+        self._lattice_h = np.zeros((0, self._n_dimensions), dtype=np.int64)
         self._scalar = pt.zeros(1, dtype=pt.float64, device=self._device)
         self._geom_table = GeometryTable(self._geometry, self._device)
 
@@ -168,6 +176,9 @@ class SamplingTree(object):
         iv = np.zeros(new_cap, dtype=bool)
         iv[:self._invalid_h.size] = self._invalid_h
         self._invalid_h = iv
+        la = np.zeros((new_cap, d), dtype=np.int64)
+        la[:self._lattice_h.shape[0]] = self._lattice_h
+        self._lattice_h = la
         self._cap = new_cap
 
     # ------------------------------------------------------------------------------------------ root cell
@@ -211,6 +222,8 @@ class SamplingTree(object):
         self._flags[0] = FLAG_LEAF
         self._n_cells = 1
         self._leaf_cells.add(0)
+        if self._cell_lookup is not None:
+            self._cell_lookup[(0,) + (0,) * d] = 0
 
     # ------------------------------------------------------------------------------------------ refinement
     def _refine_cells(self, parents: list) -> range:
@@ -232,6 +245,15 @@ class SamplingTree(object):
                                                first, n_new, self._k, self._width, self._gain0, self._sdm_order,
                                                _lib.ptr(self._metric_d), _lib.ptr(self._gain), self._stream()))
         self._levels_h[first:first + n_new] = np.repeat(self._levels_h[par_h] + 1, self._nch)
+        if self._cell_lookup is not None and n_par:
+            # host mirror of the integer lattice position (child = 2 * parent + [direction > 0]) for neighbour look-ups
+            d = self._n_dimensions
+            pos = (self._child_dirs() > 0).astype(np.int64)                                    # [2^d, d]
+            lat = (2 * self._lattice_h[par_h][:, None, :] + pos[None, :, :]).reshape(-1, d)
+            self._lattice_h[first:first + n_new] = lat
+            lv = self._levels_h[first:first + n_new]
+            for t in range(n_new):
+                self._cell_lookup[(int(lv[t]),) + tuple(int(v) for v in lat[t])] = first + t
         if n_par:
             self._current_max_level = max(self._current_max_level, int(self._levels_h[par_h].max()) + 1)
 
@@ -246,6 +268,50 @@ class SamplingTree(object):
         self._leaf_cells.update(all_children)
         self._n_cells += n_new
         return range(first, first + n_new)
+
+    def _child_dirs(self) -> np.ndarray:
+        if self._n_dimensions == 2:
+            return np.array([[-1, -1], [-1, 1], [1, 1], [1, -1]], dtype=np.int64)
+        return np.array([[-1, -1, 1], [-1, 1, 1], [1, 1, 1], [1, -1, 1], [-1, -1, -1], [-1, 1, -1], [1, 1, -1],
+                         [1, -1, -1]], dtype=np.int64)
+
+    # ------------------------------------------------------------------------------------------ delta-level constraint
+    def _check_nb(self, _cell_no: int) -> list:
+        """
+        Leaf neighbours of a cell (8 / 26 directions, reference order) with a lower level: refining the cell alone would
+        create a level difference of two (s_cube.py:447-464). The neighbour in a direction is the leaf covering the
+        adjacent same-level lattice position -- the geometric meaning of the reference's neighbour pointers.
+        """
+        lv = int(self._levels_h[_cell_no])
+        pos = self._lattice_h[_cell_no]
+        out = []
+        for dvec in self._nb_dirs:
+            q = pos + dvec
+            if (q < 0).any() or (q >= (1 << lv)).any():
+                continue
+            for up in range(0, lv + 1):
+                key = (lv - up,) + tuple(int(v) >> up for v in q)
+                c = self._cell_lookup.get(key)
+                if c is None:
+                    continue
+                # first existing ancestor-or-self of the adjacent position: a coarser leaf forces refinement
+                if up > 0 and c in self._leaf_cells:
+                    out.append(c)
+                break
+        return out
+
+    def _check_constraint(self, nb_violating_constraint: set) -> set:
+        # s_cube.py:466-506: transitive closure of the constraint over the neighbours that get refined as well
+        new_cells_to_check = True if nb_violating_constraint else False
+        while new_cells_to_check:
+            tmp = set()
+            for c in nb_violating_constraint:
+                tmp.update(self._check_nb(c))
+            if not tmp or tmp.issubset(nb_violating_constraint):
+                new_cells_to_check = False
+            else:
+                nb_violating_constraint.update(tmp)
+        return nb_violating_constraint
 
     def _mask(self, cells, refine_geometry: bool, geometry_no) -> np.ndarray:
         """
@@ -410,6 +476,9 @@ class SamplingTree(object):
             to_refine = set()
             for i in _leaf_cells_sorted:
                 to_refine.add(i)
+                if self._max_delta_level:
+                    nb_to_refine_as_well = set(self._check_nb(i))
+                    to_refine.update(self._check_constraint(nb_to_refine_as_well))
             self._remove_invalid_cells(self._refine_cells(list(to_refine)))
 
             if self._n_cells_max is None:
@@ -463,10 +532,17 @@ class SamplingTree(object):
 
             while _global_max_level > _global_min_level:
                 logger.info(f"\r\t\t\t\t\t\t\t\t\tRefining level {_global_min_level + 1} / {_global_max_level}.")
-                to_refine = set()
+                to_refine, checked = set(), set()
                 for i in _all_cells:
+                    if i in checked:
+                        continue
                     if self._levels_h[i] < _global_max_level:
                         to_refine.add(i)
+                    if self._max_delta_level:
+                        nb_to_refine_as_well = set(self._check_nb(i))
+                        nb_to_refine_as_well.update(self._check_constraint(nb_to_refine_as_well))
+                        to_refine.update(nb_to_refine_as_well)
+                        checked.update(nb_to_refine_as_well)
                 new_cells = self._refine_cells(list(to_refine))
                 _idx_new = {c for c in new_cells}
                 # children are only tested against the geometry being refined (s_cube.py:850)

@@ -85,6 +85,18 @@ def case_definitions(geo):
                          g.PyramidGeometry3D("pyr", False, [[1.2, 1.4, 0.0], [2.0, 1.4, 0.0], [2.0, 2.0, 0.0],
                                                             [1.2, 2.0, 0.0], [1.6, 1.7, 0.9]])],
         kwargs=dict(uniform_level=3, min_metric=0.5, n_cells_iter_start=10))
+    # delta-level constraint in the metric-based loop (s_cube.py:447-506, 611-618). No geometry refinement here: in
+    # that phase the reference follows neighbour pointers that can be stale (a child inherits the wrong sibling of a
+    # neighbour refined after the pointer was set), which the geometric restatement does not reproduce -- DESIGN.md 6.
+    x = synth.cylinder2d_cloud(4000, seed=8)
+    cases["g2d_delta"] = dict(
+        coords=x, metric=synth.wake_metric(x),
+        geoms=lambda g: [g.CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"]),
+                         g.SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"])],
+        kwargs=dict(uniform_level=3, min_metric=0.6, n_cells_iter_start=10, max_delta_level=True))
+    # (A 3-D delta-level case is deliberately absent: there the reference's pointer graph goes stale already in the
+    # metric-based loop -- level-4 cells in the wake drag level-2 cells at the far domain boundary into the refinement
+    # set -- so the reference and the geometric restatement differ)
     return cases
 
 
@@ -201,9 +213,13 @@ def main():
     sys.path[:0] = [stubs, REF, ROOT]
     os.environ["PYTHONPATH"] = os.pathsep.join([stubs, REF, ROOT, os.environ.get("PYTHONPATH", "")])
     import sparseSpatialSampling.geometry as geo_ref
-    np.savez_compressed(os.path.join(HERE, "geometry_pins.npz"), **geometry_pins(geo_ref))
+    if not [a for a in sys.argv[1:] if not a.startswith("-")]:
+        np.savez_compressed(os.path.join(HERE, "geometry_pins.npz"), **geometry_pins(geo_ref))
     cases = case_definitions(geo_ref)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name, case in cases.items():
+        if only and name not in only:
+            continue
         print(f"== reference run: {name} ({case['coords'].shape[0]} points)")
         _, out = run_reference_case(name, case, geo_ref)
         check_oracle_against_reference(name, case, geo_ref, out)

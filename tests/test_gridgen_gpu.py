@@ -27,7 +27,7 @@ def _run(case, **extra):
     return tree
 
 
-@pytest.mark.parametrize("name", ["g2d_metric", "g2d_ncells", "g3d_metric"])
+@pytest.mark.parametrize("name", ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta"])
 def test_refine_matches_reference_golden(cuda, name):
     import sparsespatialsampling_b200.geometry as geo
     case = case_definitions(geo)[name]
