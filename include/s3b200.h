@@ -35,7 +35,9 @@ int s3_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t s3_launch_count(void);
 
-/* tuning knobs (benchmarking): key 0 = cells per CTA of the direct interpolation kernel */
+/* tuning knobs (benchmarking): key 0 = cells per CTA of the direct interpolation kernel, ...,
+ * key 10 = 16-row K-blocks accumulated in TMEM per segment of the tensor-core Gram kernel (default 4),
+ * key 11 = segments summed in fp32 registers per fp64 flush (default 32) */
 int s3_set_tuning(int key, int value);
 
 /* ---- k-nearest-neighbour index over the original point cloud ---------------------------------
@@ -160,6 +162,26 @@ int s3_interp_pipelined(const float* d_data, int64_t n_src, int64_t row_len, con
                         const int32_t* d_tile_nrows, const uint16_t* d_tile_lidx, const float* d_w,
                         int64_t n_cells, int k, int max_rows, int chunk_cols, int stage_rows, int n_ctas,
                         int use_gather4, const int32_t* d_out_row, float* d_out, void* stream);
+
+/* ---- volume-weighted snapshot SVD ---------------------------------------------------------------
+ * device side of compute_svd (sparseSpatialSampling/utils.py:302-346), method of snapshots:
+ *   B = sqrt(vol) * (A - mean_t(A));  G = B^T B;  G = V diag(s^2) V^T (host, T x T);  U = (A - mean) V / s.
+ * A: fp32 [m, t] row-major (vector fields stacked as m = n_cells * D rows, utils.py:337-338), one weight per
+ * `vol_div` consecutive rows (vol_div = D).                                                          */
+
+/* temporal mean of every row (utils.py:322): d_mean fp32 [m] */
+int s3_svd_row_means(const float* d_a, int64_t m, int64_t t, float* d_mean, void* stream);
+/* Gram matrix of the centred, sqrt(volume)-scaled rows (utils.py:322-329 followed by the contraction the
+ * reference leaves to LAPACK): d_gram fp64 [t, t] (symmetric, both triangles written).
+ * method 1: tcgen05 tensor cores with a 3xTF32 split (fp32-equivalent products), short fp32 accumulation
+ *           segments in TMEM, summed in registers and in fp64 across flushes;  method 2: same, single TF32 products;
+ * method 0: fp32 CUDA-core tiles (cross-check).                                                      */
+int s3_svd_gram(const float* d_a, const float* d_mean, const float* d_vol, int vol_div, int64_t m, int64_t t,
+                int method, double* d_gram, void* stream);
+/* modes (utils.py:330 / :344 after the un-scaling): d_u fp32 [m, r] = (A - mean) * d_vs, d_vs fp32 [t, r] =
+ * V[:, :r] / s[:r]                                                                                    */
+int s3_svd_project(const float* d_a, const float* d_mean, const float* d_vs, int64_t m, int64_t t, int r,
+                   float* d_u, void* stream);
 
 #ifdef __cplusplus
 }

@@ -502,3 +502,44 @@ def interpolate_torch(weights, idx, data, chunk_size: int = 100000):
         rows = data.index_select(0, idx[s:e].reshape(-1)).reshape(e - s, k, data.shape[1], data.shape[2])
         out[s:e] = (rows * weights[s:e].reshape(e - s, k, 1, 1)).sum(dim=1)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- weighted SVD
+def cell_area(size_initial_cell: float, levels: np.ndarray, n_dims: int) -> np.ndarray:
+    """Dataloader._compute_cell_area (data.py:240-247): (size_initial_cell / 2^level)^d per cell."""
+    return np.power(size_initial_cell / np.power(2.0, np.asarray(levels, dtype=np.float64)), n_dims).squeeze()
+
+
+def compute_svd(data_matrix: np.ndarray, area: np.ndarray, rank: int = None):
+    """compute_svd (utils.py:302-346) in the reference's order of operations and dtype (fp32 in, fp32 SVD):
+    subtract the temporal mean (:322), scale rows by sqrt(cell_area) (:326 / :335), stack vector components to
+    (N_cells * D, T) rows (:337-338), thin SVD truncated to `rank` (:328 / :341 -- flowtorch.analysis.SVD is
+    torch.linalg.svd(full_matrices=False) followed by truncation; flowtorch, branch `aweiner`, is not vendored, so the
+    rank=None rule is not restated and an explicit rank is required), un-scale U (:330 / :344-346).
+    Returns (s [r], U [N_cells, r] | [N_cells, D, r], V [T, r]). PARITY UNPINNED by reference tests (none cover it);
+    pinned against numpy's fp64 SVD in tests/test_oracle.py."""
+    assert rank is not None, "the oracle needs an explicit rank"
+    a = np.array(data_matrix, dtype=np.float32, copy=True)
+    w = np.sqrt(np.asarray(area, dtype=np.float32))
+    a -= a.mean(axis=-1, keepdims=True, dtype=np.float32)
+    if a.ndim == 2:
+        a *= w[:, None]
+        u, s, vh = np.linalg.svd(a, full_matrices=False)
+        r = min(rank, s.shape[0])
+        return s[:r], u[:, :r] / w[:, None], vh.T[:, :r]
+    a *= w[:, None, None]
+    shape = a.shape
+    u, s, vh = np.linalg.svd(a.reshape(shape[0] * shape[1], shape[2]), full_matrices=False)
+    r = min(rank, s.shape[0])
+    return s[:r], u[:, :r].reshape(shape[0], shape[1], r) / w[:, None, None], vh.T[:, :r]
+
+
+def weighted_gram(data_matrix: np.ndarray, area: np.ndarray) -> np.ndarray:
+    """fp64 Gram matrix of the centred, sqrt(area)-weighted rows: the quantity the device contraction computes."""
+    a = np.asarray(data_matrix, dtype=np.float64)
+    if a.ndim == 3:
+        area = np.repeat(np.asarray(area, dtype=np.float64), a.shape[1])
+        a = a.reshape(a.shape[0] * a.shape[1], a.shape[2])
+    mean32 = np.asarray(data_matrix, dtype=np.float32).reshape(a.shape).mean(axis=1, dtype=np.float64).astype(np.float32)
+    b = (a.astype(np.float32) - mean32[:, None]).astype(np.float64) * np.sqrt(np.asarray(area, dtype=np.float32)).astype(np.float64)[:, None]
+    return b.T @ b

@@ -18,6 +18,8 @@ namespace s3 {
 extern int g_staging;
 extern int g_stage_budget_kb;
 extern int g_pipe_prefetch;
+extern int g_tc_seg_kblocks;
+extern int g_tc_flush_segments;
 constexpr int kInterpThreads = 128;
 constexpr int kMaxCellsPerCta = 32;
 static int g_cells_per_cta = 4;
@@ -258,6 +260,16 @@ extern "C" int s3_set_tuning(int key, int value) {
     if (key == 2) {
         S3_REQUIRE(value >= 8 && value <= 200, "s3_set_tuning: staging budget must be 8..200 KB");
         s3::g_stage_budget_kb = value;
+        return S3_OK;
+    }
+    if (key == 10) {
+        S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3_set_tuning: K-blocks per TMEM segment must be >= 1");
+        s3::g_tc_seg_kblocks = value;
+        return S3_OK;
+    }
+    if (key == 11) {
+        S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3_set_tuning: segments per fp64 flush must be >= 1");
+        s3::g_tc_flush_segments = value;
         return S3_OK;
     }
     s3::set_error("s3_set_tuning: unknown key %d", key);

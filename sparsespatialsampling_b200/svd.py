@@ -1,0 +1,140 @@
+"""
+Volume-weighted SVD of the sampled snapshots on the GPU.
+
+``compute_svd(data_matrix, cell_area, rank)`` keeps the signature and the return values ``(s, U, V)`` of the reference
+(sparseSpatialSampling/utils.py:302-346): subtract the temporal mean, weight every cell by ``sqrt(cell_area)``, thin
+SVD, un-weight the modes; vector fields ``[N_cells, D, T]`` are stacked to ``(N_cells * D, T)`` rows
+(utils.py:337-338) and the modes reshaped back (utils.py:344-346).
+
+The reference hands the weighted matrix to ``flowtorch.analysis.SVD`` (LAPACK ``gesdd`` through ``torch.linalg.svd``).
+Here the tall-skinny problem is solved by the method of snapshots -- the data matrix is read twice and never copied:
+
+    G = B^T B                 s3_svd_gram     tcgen05 tensor cores, 3xTF32 split, fp64 across K segments
+    G = V diag(s^2) V^T       torch.linalg.eigh on the device, fp64, T x T (the only library call)
+    U = (A - mean) V / s      s3_svd_project  (the sqrt(volume) scaling cancels against the un-weighting)
+
+Differences to the reference, stated: ``data_matrix`` is NOT modified in place; singular values far below
+``sqrt(eps_fp32) * s[0]`` lose relative accuracy (the Gram matrix squares the condition number), modes whose singular
+value is below ``1e-6 * s[0]`` are returned as zeros; ``rank=None`` uses the optimal hard threshold of Gavish & Donoho
+(2014) -- flowtorch's own ``opt_rank`` is not vendored with the reference (requirements.txt:5), so that case is
+unpinned. There is no CPU fallback.
+"""
+import logging
+import math
+from typing import Tuple
+
+import torch as pt
+
+from . import _lib
+
+logger = logging.getLogger(__name__)
+
+GRAM_METHODS = {"simt": 0, "tc3": 1, "tc": 2}
+
+
+def optimal_rank(s: pt.Tensor, rows: int, cols: int) -> int:
+    """Optimal hard threshold for singular values, unknown noise level (Gavish & Donoho 2014, eq. 5):
+    rank = #{s_i > omega(beta) * median(s)}, omega(beta) ~ 0.56 b^3 - 0.95 b^2 + 1.82 b + 1.43, beta = min/max."""
+    beta = min(rows, cols) / max(rows, cols)
+    omega = 0.56 * beta ** 3 - 0.95 * beta ** 2 + 1.82 * beta + 1.43
+    tau = omega * float(pt.median(s))
+    return max(1, int((s > tau).sum()))
+
+
+def _as_device_matrix(data_matrix: pt.Tensor, dev) -> pt.Tensor:
+    a = data_matrix.detach()
+    if a.dtype != pt.float32:
+        a = a.to(pt.float32)
+    if a.device != dev:
+        a = a.pin_memory().to(dev, non_blocking=True) if a.device.type == "cpu" else a.to(dev)
+    return a.contiguous()
+
+
+def row_means(a: pt.Tensor) -> pt.Tensor:
+    """Temporal mean of every row of ``a`` ([M, T] fp32 on the device)."""
+    lib = _lib.load()
+    mean = pt.empty((a.size(0),), dtype=pt.float32, device=a.device)
+    with pt.cuda.device(a.device):
+        _lib.check(lib.s3_svd_row_means(_lib.ptr(a), a.size(0), a.size(1), _lib.ptr(mean), _lib.stream_ptr()))
+    return mean
+
+
+def gram(a: pt.Tensor, mean: pt.Tensor, vol: pt.Tensor, vol_div: int = 1, method: str = "tc3") -> pt.Tensor:
+    """G[i, j] = sum_m vol[m // vol_div] (a[m, i] - mean[m]) (a[m, j] - mean[m]), fp64 [T, T]."""
+    lib = _lib.load()
+    t = a.size(1)
+    g = pt.empty((t, t), dtype=pt.float64, device=a.device)
+    with pt.cuda.device(a.device):
+        _lib.check(lib.s3_svd_gram(_lib.ptr(a), _lib.ptr(mean), _lib.ptr(vol), vol_div, a.size(0), t,
+                                   GRAM_METHODS[method], _lib.ptr(g), _lib.stream_ptr()))
+    return g
+
+
+def project(a: pt.Tensor, mean: pt.Tensor, vs: pt.Tensor) -> pt.Tensor:
+    """U = (a - mean[:, None]) @ vs, fp32 [M, r]."""
+    lib = _lib.load()
+    vs = vs.to(pt.float32).contiguous()
+    u = pt.empty((a.size(0), vs.size(1)), dtype=pt.float32, device=a.device)
+    with pt.cuda.device(a.device):
+        _lib.check(lib.s3_svd_project(_lib.ptr(a), _lib.ptr(mean), _lib.ptr(vs), a.size(0), a.size(1), vs.size(1),
+                                      _lib.ptr(u), _lib.stream_ptr()))
+    return u
+
+
+def compute_svd(data_matrix: pt.Tensor, cell_area: pt.Tensor, rank: int = None, method: str = "tc3",
+                n_modes: int = None, device=None) -> Tuple[pt.Tensor, pt.Tensor, pt.Tensor]:
+    """
+    Weighted SVD of a field (utils.py:302-346).
+
+    :param data_matrix: ``[N_cells, T]`` or ``[N_cells, D, T]``; host or device tensor (not modified)
+    :param cell_area: area (2D) / volume (3D) of every cell, ``[N_cells]``
+    :param rank: number of singular triplets to keep; ``None`` = optimal hard threshold
+    :param method: Gram kernel, ``"tc3"`` (tensor cores, 3xTF32, default), ``"tc"`` (single TF32), ``"simt"`` (fp32 cores)
+    :param n_modes: compute only the first ``n_modes`` columns of U (``s`` and ``V`` keep ``rank`` entries); used by
+        ``write_svd_s_cube_to_file``, which writes only that many modes
+    :return: ``(s [r], U [N_cells, r] | [N_cells, D, r], V [T, r])`` on the device of ``data_matrix``
+    """
+    _lib.require_cuda()
+    if method not in GRAM_METHODS:
+        raise ValueError(f"unknown Gram method '{method}', available: {sorted(GRAM_METHODS)}")
+    shape = tuple(data_matrix.shape)
+    if len(shape) not in (2, 3):
+        raise ValueError(f"data_matrix must be [N_cells, T] or [N_cells, D, T], got {shape}")
+    if cell_area.numel() != shape[0]:
+        raise ValueError(f"cell_area has {cell_area.numel()} entries for {shape[0]} cells")
+    home = data_matrix.device
+    dev = pt.device(device) if device is not None else (home if home.type == "cuda" else pt.device("cuda", pt.cuda.current_device()))
+    n_cells, t = shape[0], shape[-1]
+    vol_div = 1 if len(shape) == 2 else shape[1]
+    a = _as_device_matrix(data_matrix, dev).reshape(n_cells * vol_div, t)
+    vol = cell_area.detach().reshape(-1).to(device=dev, dtype=pt.float32).contiguous()
+
+    mean = row_means(a)
+    g = gram(a, mean, vol, vol_div, method)
+    lam, vec = pt.linalg.eigh(g)                       # ascending, fp64
+    lam = pt.flip(lam, dims=(0,))
+    vec = pt.flip(vec, dims=(1,))
+    s_all = lam.clamp_min(0.0).sqrt()
+    r_max = min(a.size(0), t)
+    if rank is None:
+        r = optimal_rank(s_all[:r_max], a.size(0), t)
+    else:
+        r = max(1, min(int(rank), r_max))
+    s = s_all[:r]
+    v = vec[:, :r]
+    r_u = r if n_modes is None else max(1, min(int(n_modes), r))
+    live = s[:r_u] > 1e-6 * float(s_all[0]) if float(s_all[0]) > 0 else pt.zeros(r_u, dtype=pt.bool, device=dev)
+    inv_s = pt.where(live, 1.0 / s[:r_u].clamp_min(1e-300), pt.zeros_like(s[:r_u]))
+    u = project(a, mean, v[:, :r_u] * inv_s.unsqueeze(0))
+    if len(shape) == 3:
+        u = u.reshape(n_cells, vol_div, r_u)
+    s_out, v_out = s.to(pt.float32), v.to(pt.float32)
+    if home != dev:
+        pt.cuda.synchronize(dev)
+        return s_out.to(home), u.to(home), v_out.to(home)
+    return s_out, u, v_out
+
+
+def svd_flops(m: int, t: int) -> float:
+    """Useful floating point operations of the Gram contraction (full square, 2*M*T^2)."""
+    return 2.0 * m * t * t

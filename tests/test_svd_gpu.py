@@ -1,0 +1,104 @@
+"""GPU parity: weighted SVD (s3_svd_row_means / s3_svd_gram / s3_svd_project, compute_svd) against the CPU oracle of
+compute_svd (utils.py:302-346)."""
+import numpy as np
+import pytest
+import torch as pt
+
+from oracle import s3_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# tolerances: leading singular values rel 1e-4, modes |<u, u_ref>| >= 1 - 1e-4 for well separated modes
+RTOL_S = 1e-4
+MODE_COS = 1.0 - 1e-4
+
+
+def _low_rank_field(n_cells, t, n_modes, seed, d=None, noise=1e-3):
+    """Snapshots with a few well separated coherent modes + small noise + a large mean, fp32."""
+    rng = np.random.default_rng(seed)
+    shape = (n_cells,) if d is None else (n_cells, d)
+    time = np.linspace(0, 2 * np.pi, t, endpoint=False)
+    a = np.zeros(shape + (t,))
+    for i in range(n_modes):
+        phi = rng.standard_normal(shape)
+        a += (2.0 ** -i) * phi[..., None] * np.cos((i + 1) * time + rng.random())
+    a += noise * rng.standard_normal(a.shape) + 3.0 + rng.standard_normal(shape)[..., None]
+    area = 2.0 ** -rng.integers(8, 16, n_cells).astype(np.float64)
+    return a.astype(np.float32), area.astype(np.float32)
+
+
+@pytest.mark.parametrize("method", ["simt", "tc3", "tc"])
+@pytest.mark.parametrize("m,t", [(3000, 100), (5000, 256), (2500, 301), (1000, 640), (17, 40)])
+def test_gram_matches_fp64(cuda, method, m, t):
+    from sparsespatialsampling_b200 import svd
+    a, area = _low_rank_field(m, t, 5, m + t)
+    ref = orc.weighted_gram(a, area)
+    ad = pt.from_numpy(a).cuda()
+    mean = svd.row_means(ad)
+    assert np.allclose(mean.cpu().numpy(), a.mean(axis=1, dtype=np.float64), rtol=1e-6, atol=1e-7)
+    g = svd.gram(ad, mean, pt.from_numpy(area).cuda(), 1, method).cpu().numpy()
+    assert np.array_equal(g, g.T)
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    tol = {"simt": 2e-5, "tc3": 5e-6, "tc": 3e-3}[method]
+    # the mean is rounded to fp32 on both sides; fp32 products/accumulation inside a segment bound the rest
+    assert (np.abs(g - ref) <= tol * scale + 1e-30).all(), float((np.abs(g - ref) / (scale + 1e-300)).max())
+
+
+def test_gram_many_rows_segments_and_splits(cuda):
+    """K range long enough for several TMEM accumulation segments per CTA (tuning key 10 shrinks the segment)."""
+    from sparsespatialsampling_b200 import svd, _lib
+    a, area = _low_rank_field(40000, 200, 4, 11)
+    ref = orc.weighted_gram(a, area)
+    ad = pt.from_numpy(a).cuda()
+    mean = svd.row_means(ad)
+    vol = pt.from_numpy(area).cuda()
+    lib = _lib.load()
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    try:
+        for seg, flush in ((1, 1), (3, 5), (4, 32), (7, 1000)):
+            _lib.check(lib.s3_set_tuning(10, seg))
+            _lib.check(lib.s3_set_tuning(11, flush))
+            g = svd.gram(ad, mean, vol, 1, "tc3").cpu().numpy()
+            assert (np.abs(g - ref) <= 5e-6 * scale).all(), (seg, flush, float((np.abs(g - ref) / scale).max()))
+    finally:
+        _lib.check(lib.s3_set_tuning(10, 4))
+        _lib.check(lib.s3_set_tuning(11, 32))
+
+
+@pytest.mark.parametrize("d", [None, 2, 3])
+@pytest.mark.parametrize("method", ["tc3", "simt"])
+def test_compute_svd_against_oracle(cuda, d, method):
+    from sparsespatialsampling_b200.svd import compute_svd
+    n_cells, t, r = 4000, 120, 6
+    a, area = _low_rank_field(n_cells, t, 4, 5, d)
+    s_ref, u_ref, v_ref = orc.compute_svd(a, area, rank=r)
+    keep = a.copy()
+    s, u, v = compute_svd(pt.from_numpy(a), pt.from_numpy(area), rank=r, method=method)
+    assert np.array_equal(a, keep), "compute_svd must not modify its input"
+    assert s.device.type == "cpu" and tuple(u.shape) == u_ref.shape and tuple(v.shape) == v_ref.shape
+    s, u, v = s.numpy(), u.numpy().astype(np.float64), v.numpy().astype(np.float64)
+    # 4 coherent modes stand clear of the noise floor
+    assert np.allclose(s[:4], s_ref[:4], rtol=RTOL_S)
+    w = np.sqrt(area.astype(np.float64))
+    w = w[:, None] if d is None else w[:, None, None]
+    for i in range(4):
+        uw, uw_ref = (u[..., i:i + 1] * w).ravel(), (u_ref[..., i:i + 1].astype(np.float64) * w).ravel()
+        assert abs(np.dot(uw, uw_ref)) / (np.linalg.norm(uw) * np.linalg.norm(uw_ref)) >= MODE_COS
+        assert abs(np.dot(v[:, i], v_ref[:, i])) >= MODE_COS
+        assert abs(np.linalg.norm(uw) - 1.0) < 1e-3           # weighted modes are orthonormal
+    # reconstruction of the centred field from the kept triplets matches the oracle's
+    flat = (n_cells * (d or 1), t)
+    rec = (u.reshape(flat[0], -1) * s[None, :]) @ v.T
+    rec_ref = (u_ref.astype(np.float64).reshape(flat[0], -1) * s_ref[None, :]) @ v_ref.T
+    assert np.abs(rec - rec_ref).max() <= 1e-3 * np.abs(rec_ref).max()
+
+
+def test_compute_svd_n_modes_and_device_input(cuda):
+    from sparsespatialsampling_b200.svd import compute_svd
+    a, area = _low_rank_field(2000, 64, 3, 2)
+    s, u, v = compute_svd(pt.from_numpy(a).cuda(), pt.from_numpy(area).cuda(), rank=10, n_modes=2)
+    assert u.is_cuda and tuple(u.shape) == (2000, 2) and tuple(s.shape) == (10,) and tuple(v.shape) == (64, 10)
+    s2, _, _ = compute_svd(pt.from_numpy(a), pt.from_numpy(area), rank=None)
+    assert 3 <= s2.numel() <= 8                                # optimal hard threshold keeps the coherent modes
+    with pytest.raises(ValueError):
+        compute_svd(pt.from_numpy(a), pt.from_numpy(area[:5]), rank=3)
