@@ -1,20 +1,28 @@
 """
-Output side of the export stage: ``Datawriter`` with the interface of the reference
-(sparseSpatialSampling/data.py:303-501: ``write_data(name, data, group, time_step)``, ``write_grid``,
-``write_xdmf_file``, ``close``, ``mode``) and the same HDF5 layout (``grid/{centers,vertices,faces}``,
-``constant/*``, ``data/<time>/<field>_{center,vertices}``).
+I/O side of the export stage with the interface of the reference (sparseSpatialSampling/data.py):
 
-File I/O is outside the accelerated path. h5py is not part of this image; when it cannot be
-imported the writer keeps the identical group/dataset tree in memory and ``close()`` stores it with ``torch.save`` as
-``<file>.pt`` so nothing is lost and the interpolated tensors stay accessible.
+* ``Datawriter(file_path, file_name, mode, mixed)`` -- ``write_data(name, data, group, time_step)``, ``write_grid``,
+  ``write_xdmf_file``, ``close``, ``mode``, ``n_cells`` (data.py:303-501),
+* ``Dataloader(load_path, file_name, dtype)`` -- ``write_times``, ``weights``, ``vertices``, ``nodes``, ``faces``,
+  ``field_names``, ``levels``, ``metric``, ``load_snapshot`` (data.py:22-300),
+* ``XDMFWriter(file_path, file_name, grid_name, mixed).write_xdmf()`` (data.py:504-777),
+
+and the same on-disk layout: ``grid/{centers,vertices,faces}``, ``constant/*``, ``data/<time>/<field>_{center,vertices}``
+(const.py:6-17, export.py:252-299).
+
+File I/O is outside the accelerated path: this module is plain host Python. The container is
+h5py when it can be imported; this image has no h5py, in which case the identical group/dataset tree is kept as nested
+dicts of tensors and stored with ``torch.save`` as ``<file>.pt`` -- the XDMF text is generated either way and refers to
+the HDF5 file name, exactly like the reference's.
 """
 import logging
-from os.path import join
-from typing import Union
+from os.path import join, isfile
+from typing import List, Union
 
+import numpy as np
 import torch as pt
 
-from .const import CONST, GRID, DATA
+from .const import CONST, GRID, DATA, CENTERS, VERTICES, FACES
 
 logger = logging.getLogger(__name__)
 
@@ -29,9 +37,219 @@ except ImportError:                     # pragma: no cover
 def _to_numpy(data):
     if isinstance(data, pt.Tensor):
         return data.detach().cpu().numpy()
-    return data
+    return np.asarray(data)
 
 
+class _TreeStore:
+    """Group/dataset tree with the small part of the h5py API used here, backed by ``torch.save``."""
+
+    def __init__(self, path: str, mode: str):
+        self._path = path + ".pt"
+        self._mode = mode
+        self.root = {}
+        if mode in ("r", "a", "r+"):
+            if isfile(self._path):
+                self.root = pt.load(self._path, weights_only=False)
+            elif mode != "a":
+                raise FileNotFoundError(self._path)
+
+    def _node(self, path: str, create: bool = False):
+        node = self.root
+        for part in [p for p in path.split("/") if p]:
+            if part not in node:
+                if not create:
+                    return None
+                node[part] = {}
+            node = node[part]
+        return node
+
+    def keys(self, path: str = "") -> List[str]:
+        node = self._node(path)
+        return sorted(node.keys()) if isinstance(node, dict) else []      # HDF5 iterates links in name order
+
+    def has(self, path: str) -> bool:
+        return self._node(path) is not None
+
+    def read(self, path: str) -> np.ndarray:
+        node = self._node(path)
+        if node is None or isinstance(node, dict):
+            raise KeyError(path)
+        return _to_numpy(node)
+
+    def write(self, group: str, name: str, data) -> bool:
+        node = self._node(group, create=True)
+        if name in node:
+            return False
+        node[name] = data.detach().cpu().clone() if isinstance(data, pt.Tensor) else data
+        return True
+
+    def close(self) -> None:
+        if self._mode != "r":
+            pt.save(self.root, self._path)
+
+
+class _H5Store:                         # pragma: no cover - needs h5py
+    """The same small API on top of an HDF5 file."""
+
+    def __init__(self, path: str, mode: str):
+        self._file = h5py.File(path, mode)
+
+    def keys(self, path: str = "") -> List[str]:
+        node = self._file[path] if path else self._file
+        return list(node.keys())
+
+    def has(self, path: str) -> bool:
+        return path in self._file
+
+    def read(self, path: str) -> np.ndarray:
+        return self._file[path][()]
+
+    def write(self, group: str, name: str, data) -> bool:
+        grp = self._file.require_group(group)
+        if name in grp:
+            return False
+        grp.create_dataset(name, data=_to_numpy(data))
+        return True
+
+    def close(self) -> None:
+        self._file.close()
+
+
+def _open_store(file_path: str, file_name: str, mode: str):
+    full = join(file_path, file_name)
+    if HAVE_H5PY:                       # pragma: no cover
+        return _H5Store(full, mode)
+    return _TreeStore(full, mode)
+
+
+# ---------------------------------------------------------------------------------------------------- Dataloader
+class Dataloader:
+    """Reads an S^3 output file (data.py:22-300)."""
+
+    def __init__(self, load_path: str, file_name: str, dtype: pt.dtype = pt.float32):
+        self._load_path = load_path
+        self._file_name = file_name
+        self._dtype = dtype
+        self._size_initial_cell = None
+        self._reset()
+
+    def _store(self):
+        return _open_store(self._load_path, self._file_name, "r")
+
+    def _reset(self) -> None:
+        st = self._store()
+        centers = st.read(f"{GRID}/{CENTERS}")
+        self._n_cells, self._n_dimensions = centers.shape[0], centers.shape[1]
+        try:
+            self._size_initial_cell = st.read(f"{CONST}/size_initial_cell")
+        except KeyError:
+            logger.warning("Could not load initial cell size.")
+        self._write_times = None
+        self._weights = None
+        self._levels = None
+        self._metric = None
+        self._field_names = None
+        self._vertices = None
+        self._faces = None
+        self._nodes = None
+
+    def _read_tensor(self, path: str) -> pt.Tensor:
+        return pt.from_numpy(np.array(self._store().read(path)))
+
+    @property
+    def write_times(self) -> List[str]:
+        if self._write_times is None:
+            st = self._store()
+            if st.has(DATA):
+                self._write_times = st.keys(DATA)
+        return self._write_times
+
+    @property
+    def weights(self) -> pt.Tensor:
+        """cell areas (2D) / volumes (3D): (size_initial_cell / 2^level)^d  (data.py:240-247)"""
+        if self._weights is None:
+            size0 = float(np.asarray(self._size_initial_cell))
+            self._weights = pt.pow(size0 / pt.pow(2.0, self.levels.to(pt.float64)), self._n_dimensions).squeeze()
+        return self._weights
+
+    @property
+    def vertices(self) -> pt.Tensor:
+        """cell centres (the reference calls them ``vertices`` here, data.py:95-108)"""
+        if self._vertices is None:
+            self._vertices = self._read_tensor(f"{GRID}/{CENTERS}")
+        return self._vertices
+
+    @property
+    def nodes(self) -> pt.Tensor:
+        if self._nodes is None:
+            self._nodes = self._read_tensor(f"{GRID}/{VERTICES}")
+        return self._nodes
+
+    @property
+    def faces(self) -> pt.Tensor:
+        if self._faces is None:
+            self._faces = self._read_tensor(f"{GRID}/{FACES}")
+        return self._faces
+
+    @property
+    def field_names(self) -> dict:
+        if self._field_names is None:
+            st = self._store()
+            self._field_names = {t: [f.split("_")[0] for f in st.keys(f"{DATA}/{t}") if f.endswith("center")]
+                                 for t in st.keys(DATA)}
+        return self._field_names
+
+    @property
+    def levels(self) -> pt.Tensor:
+        if self._levels is None:
+            self._levels = self._read_tensor(f"{CONST}/levels").squeeze()
+        return self._levels
+
+    @property
+    def metric(self) -> pt.Tensor:
+        if self._metric is None:
+            self._metric = self._read_tensor(f"{CONST}/metric").squeeze()
+        return self._metric
+
+    @property
+    def load_path(self) -> str:
+        return self._load_path
+
+    @load_path.setter
+    def load_path(self, value: str) -> None:
+        self._load_path = value
+        self._reset()
+
+    @property
+    def file_name(self) -> str:
+        return self._file_name
+
+    @file_name.setter
+    def file_name(self, value: str) -> None:
+        self._file_name = value
+        self._reset()
+
+    def load_snapshot(self, field_name: Union[List[str], str],
+                      write_times: Union[str, List[str]] = None) -> Union[List[pt.Tensor], pt.Tensor]:
+        """Data matrix ``[N_cells, T]`` (scalar) or ``[N_cells, D, T]`` (vector) of the fields at the cell centres."""
+        if write_times is None:
+            write_times = self.write_times
+        if isinstance(write_times, str):
+            write_times = [write_times]
+        if isinstance(field_name, str):
+            field_name = [field_name]
+        st = self._store()
+        matrices = []
+        for f in field_name:
+            first = st.read(f"{DATA}/{write_times[0]}/{f}_center")
+            dm = pt.zeros(tuple(first.shape) + (len(write_times),), dtype=self._dtype)
+            for i, t in enumerate(write_times):
+                dm[..., i] = pt.from_numpy(np.array(st.read(f"{DATA}/{t}/{f}_center")))
+            matrices.append(dm)
+        return matrices[0] if len(matrices) == 1 else matrices
+
+
+# ---------------------------------------------------------------------------------------------------- Datawriter
 class Datawriter:
     def __init__(self, file_path: str, file_name: str, mode: str = "w", mixed: bool = False):
         self._file_name = file_name
@@ -40,17 +258,8 @@ class Datawriter:
         self._mixed = mixed
         self._n_cells = None
         self._closed = False
-        if HAVE_H5PY:
-            self._file = h5py.File(join(file_path, file_name), mode)
-            self._tree = None
-        else:
-            self._file = None
-            self._tree = {}
-            if mode == "a":
-                try:
-                    self._tree = pt.load(join(file_path, file_name + ".pt"), weights_only=False)
-                except FileNotFoundError:
-                    pass
+        self._store = _open_store(file_path, file_name, mode)
+        if not HAVE_H5PY:
             logger.warning("h5py is not installed: writing the HDF5 tree as a torch file "
                            f"{join(file_path, file_name)}.pt instead.")
 
@@ -69,48 +278,29 @@ class Datawriter:
             path = GRID
         else:
             raise ValueError(f"Unknown group type, available types are '{DATA}', '{CONST}' and '{GRID}'.")
-        self._put(path, name, data)
-
-    def _put(self, path: str, name: str, data) -> None:
-        if self._file is not None:
-            grp = self._file.require_group(path)
-            if name in grp:
-                logger.warning(f"Field {name} already exists in {path}. Skipping field {name}.")
-                return
-            grp.create_dataset(name, data=_to_numpy(data))
-        else:
-            node = self._tree
-            for part in path.split("/"):
-                node = node.setdefault(part, {})
-            if name in node:
-                logger.warning(f"Field {name} already exists in {path}. Skipping field {name}.")
-                return
-            node[name] = data.detach().cpu().clone() if isinstance(data, pt.Tensor) else data
+        if not self._store.write(path, name, data):
+            logger.warning(f"Field {name} already exists in {path}. Skipping field {name}.")
 
     def write_grid(self, loader) -> None:
         self._n_cells = loader.vertices.shape[0]
-        self.write_data("centers", group=GRID, data=loader.vertices)
-        self.write_data("vertices", group=GRID, data=loader.nodes)
-        self.write_data("faces", group=GRID, data=loader.faces)
+        self.write_data(CENTERS, group=GRID, data=loader.vertices)
+        self.write_data(VERTICES, group=GRID, data=loader.nodes)
+        self.write_data(FACES, group=GRID, data=loader.faces)
 
     def write_xdmf_file(self) -> None:
-        # XDMF generation belongs to the on-disk format work (next in SURVEY.md 8f); the tree is complete without it
-        logger.info(f"XDMF generation for {self._file_name} is not part of the accelerated path; skipping.")
-        self.close()
+        logger.info(f"Writing XDMF file for file {self._file_name}")
+        self.close()                    # the XDMF writer reads the finished file
+        XDMFWriter(self._file_path, self._file_name, mixed=self._mixed).write_xdmf()
 
     def close(self) -> None:
-        if self._closed:
-            return
-        if self._file is not None:
-            self._file.close()
-        else:
-            pt.save(self._tree, join(self._file_path, self._file_name + ".pt"))
-        self._closed = True
+        if not self._closed:
+            self._store.close()
+            self._closed = True
 
     @property
     def tree(self):
         """In-memory group/dataset tree (only when h5py is unavailable)."""
-        return self._tree
+        return getattr(self._store, "root", None)
 
     @property
     def mode(self) -> str:
@@ -118,10 +308,10 @@ class Datawriter:
 
     @mode.setter
     def mode(self, value) -> None:
+        self.close()
         self._mode = value
+        self._store = _open_store(self._file_path, self._file_name, value)
         self._closed = False
-        if HAVE_H5PY:
-            self._file = h5py.File(join(self._file_path, self._file_name), self._mode)
 
     @property
     def file_name(self) -> str:
@@ -134,3 +324,106 @@ class Datawriter:
     @n_cells.setter
     def n_cells(self, value: int) -> None:
         self._n_cells = value
+
+
+# ---------------------------------------------------------------------------------------------------- XDMFWriter
+class XDMFWriter:
+    """
+    XDMF (version 2) description of an S^3 file for ParaView (data.py:504-777): one ``Uniform`` grid when the file has no
+    temporal data, otherwise a temporal collection with one grid per time step; fields of ``constant`` whose first
+    dimension matches the number of cells / vertices become attributes (of the first time step in the temporal case).
+    """
+
+    def __init__(self, file_path: str, file_name: str, grid_name: str = "grid_s_cube", mixed: bool = False):
+        self._file_path = file_path
+        self._grid_name = grid_name
+        self._mixed = mixed
+        self._hdf_file_name = file_name
+        self._xdmf_file_name = f"{file_name.split('.h5')[0]}.xdmf"
+        self._store = _open_store(file_path, file_name, "r")
+        self._check_grid()
+        centers = self._store.read(f"{GRID}/{CENTERS}")
+        self._n_dimensions = centers.shape[-1]
+        self._n_cells = centers.shape[0]
+        self._n_faces = self._store.read(f"{GRID}/{FACES}").shape[0]
+        self._n_vertices = self._store.read(f"{GRID}/{VERTICES}").shape[0]
+        if mixed:
+            self._grid_type = "Mixed"
+        else:
+            self._grid_type = "Quadrilateral" if self._n_dimensions == 2 else "Hexahedron"
+        self._dims = "XY" if self._n_dimensions == 2 else "XYZ"
+
+    def _check_grid(self) -> None:
+        if not self._store.has(GRID):
+            raise RuntimeError("Found no grid in the provided HDF5 file. Unable to create XDMF file without a grid.")
+        for key, what in ((FACES, "cell faces"), (CENTERS, "cell centers"), (VERTICES, "cell vertices")):
+            if key not in self._store.keys(GRID):
+                raise RuntimeError(f"Unable to find {what} in group {GRID}. Make sure the key is present and named "
+                                   f"{key}.")
+
+    # ------------------------------------------------------------------ building blocks
+    def _topology_and_geometry(self) -> str:
+        conn = f"{self._n_faces}" if self._mixed else f"{self._n_faces} {2 ** self._n_dimensions}"
+        return (f'<Topology TopologyType="{self._grid_type}" NumberOfElements="{self._n_faces}">\n'
+                f'<DataItem Format="HDF" DataType="Int" Dimensions="{conn}">\n'
+                f'{self._hdf_file_name}:/{GRID}/{FACES}\n'
+                f'</DataItem>\n</Topology>\n'
+                f'<Geometry GeometryType="{self._dims}">\n'
+                f'<DataItem Rank="2" Dimensions="{self._n_vertices} {self._n_dimensions}" NumberType="Float" '
+                f'Precision="8" Format="HDF">\n'
+                f'{self._hdf_file_name}:/{GRID}/{VERTICES}\n'
+                f'</DataItem>\n</Geometry>\n')
+
+    def _attribute(self, name: str, path: str, shape) -> str:
+        """One attribute entry, or an empty string if the dataset lives neither on the cells nor on the vertices."""
+        if len(shape) == 0:
+            return ""
+        if shape[0] == self._n_cells:
+            center, n = "Cell", self._n_cells
+        elif shape[0] == self._n_vertices:
+            center, n = "Node", self._n_vertices
+        else:
+            logger.warning(f"Field in '{path}' with a size of {tuple(shape)} doesn't match the number of cells with "
+                           f"N_cells = {self._n_cells} or the number of vertices with N_vertices = "
+                           f"{self._n_vertices}. Skipping this field.")
+            return ""
+        width = 1 if len(shape) == 1 else shape[1]
+        return (f'<Attribute Name="{name}" AttributeType="Vector" Center="{center}">\n'
+                f'<DataItem NumberType="Float" Precision="8" Format="HDF" Dimensions="{n} {width}">\n'
+                f'{self._hdf_file_name}:/{path}\n</DataItem>\n</Attribute>\n')
+
+    def _constant_attributes(self) -> str:
+        if not self._store.has(CONST):
+            logger.info("Couldn't find any constant fields to write.")
+            return ""
+        out = []
+        for k in self._store.keys(CONST):
+            shape = np.shape(self._store.read(f"{CONST}/{k}"))
+            if len(shape) and shape[0] in (self._n_cells, self._n_vertices):
+                out.append(self._attribute(k, f"{CONST}/{k}", shape))
+        return "".join(out)
+
+    # ------------------------------------------------------------------ reference interface
+    def write_xdmf(self) -> None:
+        header = '<?xml version="1.0"?>\n<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>\n<Xdmf Version="2.0">\n'
+        parts = [header]
+        if self._store.has(DATA):
+            parts.append(f'<Domain>\n<Grid Name="{self._grid_name}" GridType="Collection" CollectionType="temporal">\n')
+            for i, t in enumerate(sorted(self._store.keys(DATA), key=lambda x: float(x))):
+                parts.append(f'<Grid Name="{self._grid_name} {t}" GridType="Uniform">\n<Time Value="{t}"/>\n')
+                parts.append(self._topology_and_geometry())
+                if i == 0:
+                    parts.append(self._constant_attributes())
+                for k in self._store.keys(f"{DATA}/{t}"):
+                    # fields are stored as <field_name>_<position>
+                    name = "_".join(k.split("_")[:-1]) if len(k.split("_")) > 1 else k
+                    parts.append(self._attribute(name, f"{DATA}/{t}/{k}", np.shape(self._store.read(f"{DATA}/{t}/{k}"))))
+                parts.append('</Grid>\n')
+            parts.append('</Grid>\n</Domain>\n</Xdmf>')
+        else:
+            parts.append(f'<Domain>\n<Grid Name="{self._grid_name}" GridType="Uniform">\n')
+            parts.append(self._topology_and_geometry())
+            parts.append(self._constant_attributes())
+            parts.append("</Grid>\n</Domain>\n</Xdmf>")
+        with open(join(self._file_path, self._xdmf_file_name), "w") as f_out:
+            f_out.write("".join(parts))

@@ -102,3 +102,44 @@ def test_compute_svd_n_modes_and_device_input(cuda):
     assert 3 <= s2.numel() <= 8                                # optimal hard threshold keeps the coherent modes
     with pytest.raises(ValueError):
         compute_svd(pt.from_numpy(a), pt.from_numpy(area[:5]), rank=3)
+
+
+def test_compute_svd_against_reference_golden(cuda):
+    """compute_svd of the reference itself (utils.py:302-346, run in the build container) on a field written by the
+    reference's Datawriter: tests/golden/io_golden.npz."""
+    import os
+    from sparsespatialsampling_b200.svd import compute_svd
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "io_golden.npz"))
+    for name in ("p", "U"):
+        s, u, v = compute_svd(pt.from_numpy(gold[f"dm_{name}"]), pt.from_numpy(gold["weights"]), rank=4)
+        s, u, v = s.numpy(), u.numpy(), v.numpy()
+        s_ref = gold[f"svd_{name}_s"]
+        assert u.shape == gold[f"svd_{name}_U"].shape
+        # compare the modes that are well above the fp32 noise floor of the reference's own SVD
+        for i in range(4):
+            if s_ref[i] < 1e-3 * s_ref[0]:
+                continue
+            assert abs(s[i] - s_ref[i]) <= RTOL_S * s_ref[0]
+            a, b = u[..., i].ravel().astype(np.float64), gold[f"svd_{name}_U"][..., i].ravel().astype(np.float64)
+            assert abs(np.dot(a, b)) / (np.linalg.norm(a) * np.linalg.norm(b)) >= MODE_COS, (name, i)
+            assert abs(np.dot(v[:, i], gold[f"svd_{name}_V"][:, i])) >= MODE_COS, (name, i)
+
+
+def test_write_svd_s_cube_to_file(cuda, tmp_path):
+    """End to end: file written by Datawriter -> Dataloader -> device SVD -> modes + XDMF (utils.py:349-413)."""
+    import os
+    from sparsespatialsampling_b200 import Dataloader, write_svd_s_cube_to_file
+    from tests.test_io_format import write_case
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = np.load(os.path.join(here, "golden", "io_golden.npz"))
+    grid = np.load(os.path.join(here, "golden", "g2d_metric.npz"))
+    write_case(str(tmp_path), gold, grid)
+    write_svd_s_cube_to_file(["p", "U"], str(tmp_path), "case", new_file=False, n_modes=3, rank=4, t_start=0.2)
+    for name in ("p", "U"):
+        out = Dataloader(str(tmp_path), f"case_{name}_svd.h5")
+        st = out._store()
+        assert sorted(st.keys("constant")) == ["V", "cell_area", "mode_1", "mode_2", "mode_3", "s"]
+        assert st.read("constant/V").shape == (5, 4) and st.read("constant/s").shape == (4,)    # t >= 0.2: 5 snapshots
+        assert st.read("constant/mode_1").shape == ((1535,) if name == "p" else (1535, 2))
+        xdmf = open(tmp_path / f"case_{name}_svd.xdmf").read()
+        assert 'Attribute Name="mode_3"' in xdmf and 'Attribute Name="cell_area"' in xdmf and "Name=\"V\"" not in xdmf
