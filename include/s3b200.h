@@ -163,6 +163,13 @@ int s3_interp_pipelined(const float* d_data, int64_t n_src, int64_t row_len, con
                         int64_t n_cells, int k, int max_rows, int chunk_cols, int stage_rows, int n_ctas,
                         int use_gather4, const int32_t* d_out_row, float* d_out, void* stream);
 
+/* ---- streaming ingest -----------------------------------------------------------------------------
+ * the reference feeds snapshot batches from host memory (export.py:128-167, utils.py:155-226). A window of the
+ * time axis of a host field [rows, T] is a pitched 2-D region: one asynchronous copy per window and direction
+ * (`kind` 0 = host to device, 1 = device to host; pinned host memory), `width`/pitches in bytes.            */
+int s3_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
+                    int64_t height, int kind, void* stream);
+
 /* ---- volume-weighted snapshot SVD ---------------------------------------------------------------
  * device side of compute_svd (sparseSpatialSampling/utils.py:302-346), method of snapshots:
  *   B = sqrt(vol) * (A - mean_t(A));  G = B^T B;  G = V diag(s^2) V^T (host, T x T);  U = (A - mean) V / s.

@@ -42,4 +42,15 @@ int s3_version(void) { return 100; }
 
 int64_t s3_launch_count(void) { return s3::g_launches.load(std::memory_order_relaxed); }
 
+int s3_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height,
+                    int kind, void* stream) {
+    S3_REQUIRE(dst && src, "s3_copy2d_async: NULL argument");
+    S3_REQUIRE(width >= 0 && height >= 0 && dst_pitch >= width && src_pitch >= width, "s3_copy2d_async: bad geometry");
+    S3_REQUIRE(kind == 0 || kind == 1, "s3_copy2d_async: kind must be 0 (host to device) or 1 (device to host)");
+    if (width == 0 || height == 0) return S3_OK;
+    S3_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)height,
+                              kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return S3_OK;
+}
+
 }  // extern "C"

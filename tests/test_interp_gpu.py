@@ -118,3 +118,41 @@ def test_staged_kernel_equals_direct_kernel(cuda, N, Nc, k, D, T, chunk):
         assert np.array_equal(got, idx[32 * t:32 * t + nc])
         nr = int(tiles.nrows[t])
         assert np.array_equal(rows[t][:nr], np.unique(idx[32 * t:32 * t + nc]))
+
+
+@pytest.mark.parametrize("D,T,chunk", [(1, 1000, 256), (2, 300, 128), (3, 77, 32), (1, 64, None)])
+def test_streamed_host_path_equals_resident_path(cuda, D, T, chunk):
+    """Pipelined host -> device -> host export over windows of the time axis (pitched copies) == one resident launch."""
+    from sparsespatialsampling_b200.export import KnnTables
+    from sparsespatialsampling_b200.knn import KnnIndex
+    rng = np.random.default_rng(D * T)
+    x = pt.from_numpy(rng.random((6000, 2)))
+    q = pt.from_numpy(rng.random((2500, 2)))
+    data = pt.from_numpy(rng.standard_normal((6000, D, T)).astype(np.float32))
+    tables = KnnTables(KnnIndex(x.cuda()), q.cuda(), 8)
+    want = tables.interpolate(data.cuda(), pt.float32).cpu()
+    got = tables.interpolate_host(data.pin_memory(), chunk_snapshots=chunk)
+    assert not got.is_cuda and got.is_pinned() and pt.equal(got, want)
+    again = tables.interpolate_host(data, out=got, chunk_snapshots=chunk)       # pageable input, buffers re-used
+    assert again.data_ptr() == got.data_ptr() and pt.equal(again, want)
+
+
+def test_export_data_streams_host_batches(cuda, tmp_path):
+    from sparsespatialsampling_b200.export import ExportData
+    rng = np.random.default_rng(5)
+    x = pt.from_numpy(rng.random((5000, 2)))
+
+    class _Grid:
+        pass
+    g = _Grid()
+    g.n_dimensions, g.faces, g.vertices, g.levels = 2, None, None, None
+    g.centers, g.metric, g.size_initial_cell = pt.from_numpy(rng.random((1500, 2))), pt.from_numpy(rng.random(5000)), 1.0
+    g.save_path, g.save_name, g.grid_name = str(tmp_path), "c", "grid"
+    data = pt.from_numpy(rng.standard_normal((5000, 2, 512)).astype(np.float32))
+    outs = []
+    for stream in (True, False):
+        exp = ExportData(g, write_times=[str(i) for i in range(512)], write_files=False, stream_host=stream)
+        exp._stream_min_elements = 0
+        exp.export(x, data, "U")
+        outs.append(exp.interpolated_fields.centers)
+    assert not outs[0].is_cuda and outs[1].is_cuda and pt.equal(outs[0], outs[1].cpu())
