@@ -235,6 +235,10 @@ def run_ours(args):
         _lib.check(_lib.load().s3_set_tuning(6, args.prefetch))
     if args.unroll:
         _lib.check(_lib.load().s3_set_tuning(5, args.unroll))
+    if args.regs >= 0:
+        _lib.check(_lib.load().s3_set_tuning(8, args.regs))
+    if args.sync >= 0:
+        _lib.check(_lib.load().s3_set_tuning(7, args.sync))
     if args.cells_per_cta:
         _lib.check(_lib.load().s3_set_tuning(0, args.cells_per_cta))
 
@@ -418,6 +422,8 @@ def main():
     ap.add_argument("--variant", type=int, default=-1, help="direct kernel: 0 = CTA walks cells, 1 = warp per cell")
     ap.add_argument("--warps", type=int, default=0, help="warp-per-cell kernel: warps (= cells) per CTA")
     ap.add_argument("--unroll", type=int, default=0, help="warp-per-cell kernel: column vectors per lane and step")
+    ap.add_argument("--regs", type=int, default=-1, help="warp-per-cell kernel: 1 = (idx, w) in registers (k = 8 | 26)")
+    ap.add_argument("--sync", type=int, default=-1, help="warp-per-cell kernel: 1 = barrier per column step")
     ap.add_argument("--stage-rows", type=int, default=0, help="pipelined kernel: rows per shared-memory stage")
     ap.add_argument("--ctas", type=int, default=0, help="pipelined kernel: persistent CTAs (0 = one per SM)")
     ap.add_argument("--prefetch", type=int, default=0, help="pipelined kernel: L2 prefetch distance in work items")

@@ -4,6 +4,7 @@ size-independent correctness checks, and prints one JSON line with the timings.
 
   python scripts/run_config.py C3 [--snapshots T] [--n-cells-max M]
   python scripts/run_config.py C4 [--snapshots T] [--n-cells-max M]
+  python scripts/run_config.py C5 [--snapshots T] [--n-cells-max M]     (STL-masked body + weighted SVD of the export)
 
 Checks (no reference run needed, all hold for any size):
   * KNN indices / weights of a random sample of cells equal the CPU oracle's brute-force search (bit-exact idx);
@@ -52,19 +53,37 @@ def config(name: str, n_cells_max):
         geoms = [geo.CubeGeometry("domain", True, synth.CYL3D["lower"], synth.CYL3D["upper"]),
                  geo.CylinderGeometry3D("cylinder", False, [[0.8, 1.0, 0.0], [0.8, 1.0, zmax]], 0.05, refine=True)]
         return x, geoms, dict(xc=0.8, yc=1.0), dict(uniform_levels=5, n_cells_max=n_cells_max or 500000)
+    if name == "C5":
+        # same cloud as C4; the body is a closed triangulated surface (icosphere, 5120 triangles) read from an STL file
+        from tests.stl_util import icosphere_triangles, write_binary_stl
+        x = synth.cylinder3d_cloud(synth.CONFIGS["C5"][0], seed=0)
+        zmax = synth.CYL3D["upper"][2]
+        stl = "/tmp/s3b200_c5_body.stl"
+        write_binary_stl(stl, icosphere_triangles(4, 0.12, (0.8, 1.0, zmax / 2)))
+        geoms = [geo.CubeGeometry("domain", True, synth.CYL3D["lower"], synth.CYL3D["upper"]),
+                 geo.GeometrySTL3D("body", False, stl, refine=True)]
+        return x, geoms, dict(xc=0.8, yc=1.0), dict(uniform_levels=5, n_cells_max=n_cells_max or 500000)
     raise SystemExit(f"unknown config {name}")
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("name", choices=["C3", "C4"])
+    ap.add_argument("name", choices=["C3", "C4", "C5"])
+    ap.add_argument("--svd", action="store_true", help="weighted SVD of the exported matrix (always on for C5)")
     ap.add_argument("--snapshots", type=int, default=0)
     ap.add_argument("--n-cells-max", type=int, default=0)
     ap.add_argument("--sample", type=int, default=512)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--tune", default="", help="comma separated key=value pairs for s3_set_tuning, e.g. 5=1,8=0")
+    ap.add_argument("--skip-grid-checks", action="store_true")
     args = ap.parse_args()
     dev = pt.device("cuda", 0)
     pt.cuda.set_device(dev)
+    if args.tune:
+        from sparsespatialsampling_b200 import _lib
+        for kv in args.tune.split(","):
+            key, val = kv.split("=")
+            _lib.check(_lib.load().s3_set_tuning(int(key), int(val)))
     x, geoms, wake, grid_kw = config(args.name, args.n_cells_max)
     d = x.size(1)
     k = 8 if d == 2 else 26
@@ -152,6 +171,52 @@ def main():
         raise AssertionError(f"linearity violated at {int(bad.sum())} of {bad.numel()} values, e.g. {i}: "
                              f"{a[i].item()!r} {b[i].item()!r}; nan: {int(pt.isnan(a).sum())} {int(pt.isnan(b).sum())}")
 
+    # ---- weighted SVD of the exported matrix (C5): device Gram vs an fp64 contraction, SVD identities
+    svd_info = None
+    if args.svd or args.name == "C5":
+        from sparsespatialsampling_b200 import svd as s3svd
+        del data
+        a2 = out.reshape(nc, T)
+        area = pt.pow(width / pt.pow(2.0, sc.levels.to(device=dev, dtype=pt.float64).reshape(-1)), d).to(pt.float32)
+        mean = s3svd.row_means(a2)
+        times = {}
+        for method in ("tc3", "tc", "simt"):
+            g = s3svd.gram(a2, mean, area, 1, method)
+            pt.cuda.synchronize()
+            g0, g1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
+            g0.record()
+            g = s3svd.gram(a2, mean, area, 1, method)
+            g1.record()
+            pt.cuda.synchronize()
+            times[method] = g0.elapsed_time(g1)
+            if method == "tc3":
+                g_tc3 = g
+        # fp64 Gram in row chunks (the fp64 copy of the whole matrix would not be needed at once)
+        g_ref = pt.zeros((T, T), dtype=pt.float64, device=dev)
+        for r0 in range(0, nc, 65536):
+            b = (a2[r0:r0 + 65536] - mean[r0:r0 + 65536, None]).double() * area[r0:r0 + 65536].sqrt().double()[:, None]
+            g_ref += b.T @ b
+        scale = pt.sqrt(pt.outer(pt.diag(g_ref), pt.diag(g_ref))).clamp_min(1e-300)
+        gram_err = float(((g_tc3 - g_ref).abs() / scale).max())
+        assert gram_err <= 5e-6, gram_err
+        t0 = time.time()
+        s_val, u, v = s3svd.compute_svd(a2, area, rank=50, n_modes=10)
+        pt.cuda.synchronize()
+        t_svd = time.time() - t0
+        lam = pt.linalg.eigvalsh(g_ref).flip(0).clamp_min(0).sqrt()[:50]
+        big = lam > 1e-2 * lam[0]
+        assert float(((s_val.double() - lam).abs() / lam)[big].max()) <= 1e-4
+        # weighted modes are orthonormal (the synthetic wake has only a handful of coherent modes: check those)
+        n_sig = max(1, min(10, int((lam > 1e-3 * lam[0]).sum())))
+        uw = u[:, :n_sig].double() * area.sqrt().double()[:, None]
+        ortho = float((uw.T @ uw - pt.eye(n_sig, dtype=pt.float64, device=dev)).abs().max())
+        assert ortho <= 1e-3, ortho
+        assert float((v.double().T @ v.double() - pt.eye(50, dtype=pt.float64, device=dev)).abs().max()) <= 1e-5
+        flop = 2.0 * nc * T * T
+        svd_info = {"matrix": [int(nc), T], "gram_ms": times, "gram_useful_tflops_tc3": flop / times["tc3"] / 1e9,
+                    "gram_max_rel_err_vs_fp64": gram_err, "compute_svd_s_rank50_10_modes": t_svd,
+                    "mode_orthonormality_err": ortho, "significant_modes": n_sig, "s_rel_err_top": float(((s_val.double() - lam).abs() / lam)[big].max())}
+
     n_unique = int(pt.unique(tables.idx_sorted).numel())
     b_algo = n_unique * T * 4 + nc * T * 4 + nc * k * 8
     peak = 6542.7
@@ -167,6 +232,7 @@ def main():
         "interp_ms": ms, "snapshot_points_per_s": nc * T / (ms * 1e-3), "unique_source_points": n_unique,
         "algorithmic_GBps": b_algo / (ms * 1e-3) / 1e9, "roofline_frac_of_measured": b_algo / (ms * 1e-3) / 1e9 / peak,
         "checks": "grid consistency, masks, knn idx/weights, interpolation tolerance, constant, linearity: ok",
+        "svd": svd_info,
     }))
 
 

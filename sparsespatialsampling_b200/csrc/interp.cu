@@ -9,6 +9,7 @@
 // of the row. The (idx, w) tile is staged into shared memory with one 1-D TMA bulk copy
 // (cp.async.bulk + mbarrier); every lane then streams 128-bit column vectors of the k source
 // rows (k independent loads in flight per thread) and writes one 128-bit result.
+#include <type_traits>
 #include "common.cuh"
 #include "tma.cuh"
 #include "../../include/s3b200.h"
@@ -25,7 +26,9 @@ constexpr int kMaxCellsPerCta = 32;
 static int g_cells_per_cta = 4;
 static int g_direct_variant = 1;   // 0 = CTA walks cells, 1 = warp per cell (s3_set_tuning key 3)
 static int g_warps_per_cta = 8;
-static int g_unroll = 2;           // column vectors per lane and step (s3_set_tuning key 5)    // warp-per-cell variant (s3_set_tuning key 4)   // tuning knob (s3_set_tuning key 0)
+static int g_direct_regs = 0;      // k = 8 / 26: (idx, w) in registers instead of shuffle broadcasts (s3_set_tuning key 8)
+static int g_direct_sync = 0;      // barrier per column step in the warp-per-cell kernel (s3_set_tuning key 7)
+static int g_unroll = 0;           // column vectors per lane and step (s3_set_tuning key 5)    // warp-per-cell variant (s3_set_tuning key 4)   // tuning knob (s3_set_tuning key 0)
 
 template <typename T, int V>
 struct alignas(sizeof(T) * V) Vec {
@@ -123,23 +126,30 @@ interp_gather_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_
 // and are served by L1 (hit or hit-under-miss) instead of crossing L2->SM once per reference; the CTAs in flight
 // cover a compact window of the grid, so the second use of a row by a neighbouring CTA is an L2 hit.
 // (idx, w) of the cell live in registers (lane j holds neighbour j) and are broadcast with shuffles.
-template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL>
-__global__ void __launch_bounds__(256)
+// SYNC: the warps of the CTA additionally meet at a barrier after every column step, so that the row segments shared by
+// neighbouring cells are requested within one step by all warps (L1 hit / hit-under-miss instead of a second fill).
+template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL, bool SYNC>
+__global__ void __launch_bounds__(512)
 interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
                        const Tw* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
                        Tout* __restrict__ out) {
     const int warps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t cell = (int64_t)blockIdx.x * warps + warp;
-    if (cell >= n_cells) return;
+    const bool active = cell < n_cells;
+    if (!SYNC && !active) return;
     int32_t idx_lo = 0, idx_hi = 0;
     Tw w_lo = (Tw)0, w_hi = (Tw)0;
-    if (lane < k) { idx_lo = idx[cell * k + lane]; w_lo = w[cell * k + lane]; }
-    if (lane + 32 < k) { idx_hi = idx[cell * k + lane + 32]; w_hi = w[cell * k + lane + 32]; }
-    const int64_t orow = out_row ? (int64_t)out_row[cell] : cell;
+    if (active && lane < k) { idx_lo = idx[cell * k + lane]; w_lo = w[cell * k + lane]; }
+    if (active && lane + 32 < k) { idx_hi = idx[cell * k + lane + 32]; w_hi = w[cell * k + lane + 32]; }
+    const int64_t orow = !active ? 0 : (out_row ? (int64_t)out_row[cell] : cell);
     Tout* o = out + orow * row_len;
     constexpr int STEP = 32 * V;
     for (int64_t col0 = 0; col0 < row_len; col0 += (int64_t)STEP * UNROLL) {
+        if (SYNC) {
+            __syncthreads();
+            if (!active) continue;
+        }
         Tw acc[UNROLL][V];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
@@ -177,6 +187,71 @@ interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int3
     }
 }
 
+// Register-resident variant for the two neighbour counts S^3 uses (k = 8 in 2-D, 26 in 3-D; s_cube.py:161,
+// export.py:117-118): every lane keeps the cell's k (index, weight) pairs in registers (uniform loads, one wavefront
+// each), so the inner loop is address arithmetic + LDG.128 + FFMA only. The shuffle-broadcast of the generic kernel
+// costs two LSU-pipe wavefronts per neighbour and column step -- a third of the wavefronts of a kernel that ncu shows
+// bound by exactly that pipe.
+template <int V, int UNROLL, int K>
+__global__ void __launch_bounds__(512)
+interp_warpcell_reg_kernel(const float* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
+                           const float* __restrict__ w, int64_t n_cells, const int32_t* __restrict__ out_row,
+                           float* __restrict__ out) {
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t cell = (int64_t)blockIdx.x * warps + warp;
+    if (cell >= n_cells) return;
+    int32_t ri[K];
+    float rw[K];
+    {
+        // K * 4 bytes per cell: 8-byte aligned for every even K
+        const int2* pi = reinterpret_cast<const int2*>(idx + cell * K);
+        const float2* pw = reinterpret_cast<const float2*>(w + cell * K);
+#pragma unroll
+        for (int j = 0; j < K / 2; ++j) {
+            const int2 a = pi[j];
+            const float2 b = pw[j];
+            ri[2 * j] = a.x; ri[2 * j + 1] = a.y;
+            rw[2 * j] = b.x; rw[2 * j + 1] = b.y;
+        }
+    }
+    const int64_t orow = out_row ? (int64_t)out_row[cell] : cell;
+    float* o = out + orow * row_len;
+    constexpr int STEP = 32 * V;
+    const float* base = data + lane * V;
+    for (int64_t col0 = 0; col0 < row_len; col0 += (int64_t)STEP * UNROLL) {
+        float acc[UNROLL][V];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[u][e] = 0.f;
+        bool in[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) in[u] = col0 + u * STEP + lane * V < row_len;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float* src = base + (int64_t)ri[j] * row_len + col0;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (in[u]) {
+                    const Vec<float, V> x = ld_stream<float, V>(src + u * STEP);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[u][e] = fmaf(rw[j], x.v[e], acc[u][e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (in[u]) {
+                Vec<float, V> ov;
+#pragma unroll
+                for (int e = 0; e < V; ++e) ov.v[e] = acc[u][e];
+                *reinterpret_cast<Vec<float, V>*>(o + col0 + u * STEP + lane * V) = ov;
+            }
+        }
+    }
+}
+
 template <typename Tin, typename Tw, typename Tout, int MODE>
 static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, const void* w, int64_t n_cells, int k,
                          const int32_t* out_row, void* out, cudaStream_t stream) {
@@ -191,16 +266,39 @@ static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, 
     if (g_direct_variant == 1 && k <= 64) {
         const int warps = g_warps_per_cta;
         const int64_t blocks = ceil_div(n_cells, warps);
+        // column vectors per lane and step: measured best 1 for k = 8 (C2/C3), 2 for k = 26 (C4/C5); 0 = this rule
+        const int unroll = g_unroll != 0 ? g_unroll : (k > 16 ? 2 : 1);
         S3_REQUIRE(blocks < ((int64_t)1 << 31), "too many cells");
-        if (vec_ok && g_unroll == 2)
-            interp_warpcell_kernel<Tin, Tw, Tout, VFULL, MODE, 2><<<(unsigned)blocks, warps * 32, 0, stream>>>(
-                reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p);
-        else if (vec_ok)
-            interp_warpcell_kernel<Tin, Tw, Tout, VFULL, MODE, 1><<<(unsigned)blocks, warps * 32, 0, stream>>>(
-                reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p);
-        else
-            interp_warpcell_kernel<Tin, Tw, Tout, 1, MODE, 2><<<(unsigned)blocks, warps * 32, 0, stream>>>(
-                reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p);
+        if (std::is_same<Tin, float>::value && std::is_same<Tout, float>::value && MODE == 0 && vec_ok &&
+            g_direct_regs != 0 && (k == 8 || k == 26)) {
+            const float* d32 = reinterpret_cast<const float*>(data);
+            const float* w32 = reinterpret_cast<const float*>(w);
+            float* o32 = reinterpret_cast<float*>(out);
+#define S3_WARPCELL_REG(UU, KK)                                                                                 \
+    interp_warpcell_reg_kernel<4, UU, KK><<<(unsigned)blocks, warps * 32, 0, stream>>>(d32, row_len, idx, w32,     \
+                                                                                         n_cells, out_row, o32)
+            if (k == 8) {
+                if (unroll == 2) S3_WARPCELL_REG(2, 8); else S3_WARPCELL_REG(1, 8);
+            } else {
+                if (unroll == 2) S3_WARPCELL_REG(2, 26); else S3_WARPCELL_REG(1, 26);
+            }
+#undef S3_WARPCELL_REG
+            S3_LAUNCH_CHECK();
+            note_launch(1);
+            return S3_OK;
+        }
+#define S3_WARPCELL(VV, UU, SS)                                                                                 \
+    interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, SS><<<(unsigned)blocks, warps * 32, 0, stream>>>(          \
+        reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p)
+        const bool sync = g_direct_sync != 0;
+        if (vec_ok && unroll == 2) {
+            if (sync) S3_WARPCELL(VFULL, 2, true); else S3_WARPCELL(VFULL, 2, false);
+        } else if (vec_ok) {
+            if (sync) S3_WARPCELL(VFULL, 1, true); else S3_WARPCELL(VFULL, 1, false);
+        } else {
+            S3_WARPCELL(1, 2, false);
+        }
+#undef S3_WARPCELL
         S3_LAUNCH_CHECK();
         note_launch(1);
         return S3_OK;
@@ -243,7 +341,7 @@ extern "C" int s3_set_tuning(int key, int value) {
         return S3_OK;
     }
     if (key == 4) {
-        S3_REQUIRE(value >= 1 && value <= 8, "s3_set_tuning: warps per CTA must be 1..8");
+        S3_REQUIRE(value >= 1 && value <= 16, "s3_set_tuning: warps per CTA must be 1..16");
         s3::g_warps_per_cta = value;
         return S3_OK;
     }
@@ -253,13 +351,23 @@ extern "C" int s3_set_tuning(int key, int value) {
         return S3_OK;
     }
     if (key == 5) {
-        S3_REQUIRE(value == 1 || value == 2, "s3_set_tuning: unroll must be 1 or 2");
+        S3_REQUIRE(value >= 0 && value <= 2, "s3_set_tuning: unroll must be 0 (auto), 1 or 2");
         s3::g_unroll = value;
         return S3_OK;
     }
     if (key == 2) {
         S3_REQUIRE(value >= 8 && value <= 200, "s3_set_tuning: staging budget must be 8..200 KB");
         s3::g_stage_budget_kb = value;
+        return S3_OK;
+    }
+    if (key == 7) {
+        S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: sync must be 0 or 1");
+        s3::g_direct_sync = value;
+        return S3_OK;
+    }
+    if (key == 8) {
+        S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: register variant must be 0 or 1");
+        s3::g_direct_regs = value;
         return S3_OK;
     }
     if (key == 10) {
