@@ -111,6 +111,8 @@ int s3_points_inside(const double* d_points, int64_t n, int dim, const int32_t* 
  * d_out int64 [k], ordered by (gain descending, index ascending). Requires k <= number of leaves.   */
 int s3_select_topk(const double* d_gain, const uint8_t* d_flags, int64_t n_cells, int64_t k,
                    int64_t* d_out, void* stream);
+/* implementation switch (tests / benchmarking): 1 = one cooperative launch for k <= 8192 (default), 0 = multi-kernel */
+int s3_select_set_fused(int on);
 
 /* final grid assembly (_resort_nodes_and_indices_of_grid, s_cube.py:734-772): corners of the leaf cells
  * `d_leaves` (int64 [n_leaves], output order) de-duplicated on the finest lattice.

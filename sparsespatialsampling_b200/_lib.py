@@ -46,6 +46,7 @@ _SIGNATURES = {
                               c_void_p]),
     "s3_points_inside": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "s3_select_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "s3_select_set_fused": (c_int, [c_int]),
     "s3_build_nodes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p,
                                POINTER(c_int64), c_void_p]),
     "s3_leaf_sumsq": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -362,6 +362,169 @@ __global__ void widen_idx_kernel(const uint32_t* __restrict__ in, int64_t n, int
     if (i < n) out[i] = (int64_t)in[i];
 }
 
+// ---------------------------------------------------------------- fused selection (one cooperative launch)
+// The adaptive loop is a chain of small dependent steps, so the 38 launches of the multi-kernel selection above cost
+// more than the work. This kernel does the whole top-k in one launch of at most one CTA per SM (cooperative launch:
+// all CTAs are co-resident, so a global barrier is legal): a radix select over the 96-bit composite key
+// (ordered gain, ~index) -- unique per cell, hence no tie handling -- in nine 11/10-bit digits with a grid barrier
+// after each histogram, an unordered append of the k winners, and a bitonic sort of the winners by CTA 0.
+constexpr int kFusedThreads = 256;
+constexpr int kFusedBins = 2048;
+constexpr int kFusedPasses = 9;
+constexpr int kFusedMaxSortK = 8192;                 // winners sorted in shared memory (12 bytes each)
+__constant__ int kFusedShift[kFusedPasses] = {85, 74, 63, 52, 42, 32, 21, 10, 0};
+__constant__ int kFusedBits[kFusedPasses] = {11, 11, 11, 11, 10, 10, 11, 11, 10};
+
+struct FusedSelectState {
+    uint32_t hist[kFusedPasses][kFusedBins];
+    uint32_t barrier;
+    uint32_t n_out;
+};
+
+struct Key96 {
+    uint64_t hi;   // ordered gain
+    uint32_t lo;   // ~index: smaller index = larger key
+};
+
+__device__ __forceinline__ uint32_t key96_digit(const Key96& k, int shift, int bits) {
+    // bits [shift, shift + bits) of the 96-bit number (hi << 32) | lo
+    const uint32_t mask = (1u << bits) - 1u;
+    if (shift >= 32) return (uint32_t)(k.hi >> (shift - 32)) & mask;
+    // digits never straddle the hi/lo boundary with the chosen widths (shift + bits <= 32 here)
+    return (k.lo >> shift) & mask;
+}
+// do the bits above `shift` of a and b agree?
+__device__ __forceinline__ bool key96_prefix_equal(const Key96& a, const Key96& b, int shift) {
+    if (shift >= 96) return true;
+    if (shift >= 32) {
+        const int s = shift - 32;
+        return s >= 64 ? true : ((a.hi >> s) == (b.hi >> s));
+    }
+    return a.hi == b.hi && (shift >= 32 ? true : ((a.lo >> shift) == (b.lo >> shift)));
+}
+__device__ __forceinline__ bool key96_ge(const Key96& a, const Key96& b) {
+    return a.hi > b.hi || (a.hi == b.hi && a.lo >= b.lo);
+}
+__device__ __forceinline__ bool key96_gt(const Key96& a, const Key96& b) {
+    return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo);
+}
+
+__device__ __forceinline__ void fused_grid_barrier(uint32_t* counter, uint32_t& generation) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t target = (generation + 1u) * gridDim.x;
+        atomicAdd(counter, 1u);
+        while (*((volatile uint32_t*)counter) < target) { }
+        __threadfence();
+    }
+    ++generation;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+select_fused_kernel(const double* __restrict__ gain, const uint8_t* __restrict__ flags, int64_t n, uint32_t k,
+                    FusedSelectState* st, uint64_t* __restrict__ win_key, uint32_t* __restrict__ win_idx,
+                    int64_t* __restrict__ out, int sort_in_kernel) {
+    extern __shared__ __align__(16) unsigned char fused_smem[];
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(fused_smem);            // [kFusedBins], re-used by the sort
+    __shared__ uint32_t s_digit, s_rem;
+    uint32_t generation = 0;
+    Key96 prefix{0ull, 0u};
+    uint32_t remaining = k;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+    for (int pass = 0; pass < kFusedPasses; ++pass) {
+        const int shift = kFusedShift[pass], bits = kFusedBits[pass];
+        for (int b = threadIdx.x; b < kFusedBins; b += blockDim.x) s_hist[b] = 0;
+        __syncthreads();
+        for (int64_t i = t0; i < n; i += stride) {
+            if (flags[i] & kFlagLeaf) {
+                const Key96 key{f64_to_ordered(gain[i]), ~(uint32_t)i};
+                if (key96_prefix_equal(key, prefix, shift + bits)) atomicAdd(&s_hist[key96_digit(key, shift, bits)], 1u);
+            }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < (1 << bits); b += blockDim.x)
+            if (s_hist[b]) atomicAdd(&st->hist[pass][b], s_hist[b]);
+        fused_grid_barrier(&st->barrier, generation);
+        // every CTA finds the digit of the remaining-th largest key from the same global histogram
+        if (threadIdx.x < 32) {
+            // warp scan from the top bin down
+            const int nb = 1 << bits;
+            const int per = nb / 32;
+            const volatile uint32_t* h = st->hist[pass];
+            uint32_t mine = 0;
+            const int hi_bin = nb - 1 - (int)threadIdx.x * per;       // lane 0 owns the top `per` bins
+            for (int j = 0; j < per; ++j) mine += h[hi_bin - j];
+            uint32_t incl = mine;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)threadIdx.x >= o) incl += v;
+            }
+            const uint32_t excl = incl - mine;                          // keys in the lanes above mine
+            if (remaining > excl && remaining <= incl) {
+                uint32_t rem = remaining - excl;
+                int digit = hi_bin;
+                for (int j = 0; j < per; ++j) {
+                    const uint32_t c = h[hi_bin - j];
+                    if (rem <= c) { digit = hi_bin - j; break; }
+                    rem -= c;
+                }
+                s_digit = (uint32_t)digit;
+                s_rem = rem;
+            }
+        }
+        __syncthreads();
+        const uint32_t digit = s_digit;
+        remaining = s_rem;
+        if (shift >= 32) prefix.hi |= (uint64_t)digit << (shift - 32);
+        else prefix.lo |= digit << shift;
+        __syncthreads();
+    }
+    // prefix is now the k-th largest composite key: every key >= prefix is a winner (exactly k of them)
+    for (int64_t i = t0; i < n; i += stride) {
+        if (flags[i] & kFlagLeaf) {
+            const Key96 key{f64_to_ordered(gain[i]), ~(uint32_t)i};
+            if (key96_ge(key, prefix)) {
+                const uint32_t pos = atomicAdd(&st->n_out, 1u);
+                if (pos < k) { win_key[pos] = key.hi; win_idx[pos] = (uint32_t)i; }
+            }
+        }
+    }
+    if (!sort_in_kernel) return;
+    fused_grid_barrier(&st->barrier, generation);
+    if (blockIdx.x != 0) return;
+    // bitonic sort of the winners, descending composite key = (gain descending, index ascending)
+    uint32_t p2 = 1;
+    while (p2 < k) p2 <<= 1;
+    uint64_t* s_hi = reinterpret_cast<uint64_t*>(fused_smem);
+    uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_hi + p2);
+    for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+        // __ldcg: written by other CTAs in this launch
+        s_hi[i] = i < k ? __ldcg(win_key + i) : 0ull;
+        s_lo[i] = i < k ? ~__ldcg(win_idx + i) : 0u;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= p2; size <<= 1) {
+        for (uint32_t strd = size >> 1; strd > 0; strd >>= 1) {
+            for (uint32_t i = threadIdx.x; i < p2 / 2; i += blockDim.x) {
+                const uint32_t lo = 2 * i - (i & (strd - 1));
+                const uint32_t hi = lo + strd;
+                const bool desc = ((lo & size) == 0);
+                const Key96 a{s_hi[lo], s_lo[lo]}, b{s_hi[hi], s_lo[hi]};
+                if (key96_gt(b, a) == desc) {
+                    s_hi[lo] = b.hi; s_lo[lo] = b.lo;
+                    s_hi[hi] = a.hi; s_lo[hi] = a.lo;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) out[i] = (int64_t)(~s_lo[i]);
+}
+
 // ---------------------------------------------------------------- captured metric (s_cube.py:317-336)
 // sum of metric^2 over the leaves; fixed reduction tree -> deterministic
 __global__ void __launch_bounds__(256)
@@ -501,13 +664,11 @@ int s3_points_inside(const double* d_points, int64_t n, int dim, const int32_t* 
     return S3_OK;
 }
 
-int s3_select_topk(const double* d_gain, const uint8_t* d_flags, int64_t n_cells, int64_t k, int64_t* d_out,
-                   void* stream) {
-    S3_REQUIRE(d_gain && d_flags && d_out, "s3_select_topk: NULL argument");
-    S3_REQUIRE(k >= 0 && k <= n_cells, "s3_select_topk: k out of range");
-    S3_REQUIRE(n_cells < ((int64_t)1 << 31), "s3_select_topk: too many cells");
-    if (k == 0) return S3_OK;
-    cudaStream_t st_ = (cudaStream_t)stream;
+static int g_select_fused = 1;     // 1 = one cooperative launch (default), 0 = multi-kernel radix select
+extern "C" int s3_select_set_fused(int on) { g_select_fused = on != 0; return S3_OK; }
+
+static int select_topk_multi(const double* d_gain, const uint8_t* d_flags, int64_t n_cells, int64_t k, int64_t* d_out,
+                             cudaStream_t st_) {
     Scratch scratch(st_);
     const int nblocks = (int)ceil_div(n_cells, kSelTile);
     SelectState* st = nullptr;
@@ -533,6 +694,47 @@ int s3_select_topk(const double* d_gain, const uint8_t* d_flags, int64_t n_cells
     note_launch(24);
     widen_idx_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, st_>>>(in_a ? ia : ib, k, d_out);
     S3_LAUNCH_CHECK();
+    note_launch(1);
+    return S3_OK;
+}
+
+int s3_select_topk(const double* d_gain, const uint8_t* d_flags, int64_t n_cells, int64_t k, int64_t* d_out,
+                   void* stream) {
+    S3_REQUIRE(d_gain && d_flags && d_out, "s3_select_topk: NULL argument");
+    S3_REQUIRE(k >= 0 && k <= n_cells, "s3_select_topk: k out of range");
+    S3_REQUIRE(n_cells < ((int64_t)1 << 31), "s3_select_topk: too many cells");
+    if (k == 0) return S3_OK;
+    cudaStream_t st_ = (cudaStream_t)stream;
+    if (!g_select_fused || k > kFusedMaxSortK) return select_topk_multi(d_gain, d_flags, n_cells, k, d_out, st_);
+
+    Scratch scratch(st_);
+    FusedSelectState* st = nullptr;
+    uint64_t* win_key = nullptr;
+    uint32_t* win_idx = nullptr;
+    S3_TRY(scratch.alloc(&st, 1));
+    S3_TRY(scratch.alloc(&win_key, k));
+    S3_TRY(scratch.alloc(&win_idx, k));
+    S3_CUDA(cudaMemsetAsync(st, 0, sizeof(FusedSelectState), st_));
+    uint32_t p2 = 1;
+    while (p2 < (uint32_t)k) p2 <<= 1;
+    size_t smem = (size_t)p2 * 12;
+    if (smem < kFusedBins * sizeof(uint32_t)) smem = kFusedBins * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        S3_CUDA(cudaFuncSetAttribute(select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kFusedMaxSortK * 12));
+        attr_set = true;
+    }
+    // enough CTAs to stream the cell arrays, never more than one per SM (co-residency of the grid barrier)
+    int grid = (int)ceil_div(n_cells, (int64_t)kFusedThreads * 8);
+    if (grid > kNumSMs) grid = kNumSMs;
+    if (grid < 1) grid = 1;
+    uint32_t k32 = (uint32_t)k;
+    int sort_in_kernel = 1;
+    void* args[] = {(void*)&d_gain, (void*)&d_flags, (void*)&n_cells, (void*)&k32, (void*)&st, (void*)&win_key,
+                    (void*)&win_idx, (void*)&d_out, (void*)&sort_in_kernel};
+    S3_CUDA(cudaLaunchCooperativeKernel((const void*)select_fused_kernel, dim3((unsigned)grid), dim3(kFusedThreads), args,
+                                        smem, st_));
     note_launch(1);
     return S3_OK;
 }

@@ -101,14 +101,21 @@ def test_refine_matches_oracle_on_fresh_inputs(cuda):
     np.testing.assert_allclose(tree.data_final_mesh["metric_per_iter"], o.metric_log, rtol=1e-12)
 
 
-def test_selection_order_matches_heapq(cuda):
-    # s3_select_topk == heapq.nlargest(k, leaves, key=(gain, -idx)) including exact gain ties
+@pytest.mark.parametrize("fused", [1, 0])
+def test_selection_order_matches_heapq(cuda, fused):
+    # s3_select_topk == heapq.nlargest(k, leaves, key=(gain, -idx)) including exact gain ties; both implementations:
+    # the single cooperative launch (default, k <= 8192) and the multi-kernel radix select + sort
     import heapq
     from sparsespatialsampling_b200 import _lib
     lib = _lib.load()
+    _lib.check(lib.s3_select_set_fused(fused))
     rng = np.random.default_rng(0)
-    for n, k in [(5000, 37), (5000, 5000), (100000, 2500), (7, 3), (3000, 1)]:
+    for n, k in [(5000, 37), (5000, 5000), (100000, 2500), (7, 3), (3000, 1), (400000, 8192), (400000, 9000),
+                 (1000, 1000), (300, 2)]:
         gain = rng.random(n)
+        if n == 300:
+            gain = -gain                                  # negative and mixed-sign gains keep their order
+            gain[::7] = 1e-300
         gain[rng.integers(0, n, n // 3)] = 0.25          # many exact ties
         gain[rng.integers(0, n, n // 10)] = 0.0
         flags = (rng.random(n) < 0.7).astype(np.uint8)
@@ -120,7 +127,8 @@ def test_selection_order_matches_heapq(cuda):
         f = pt.from_numpy(flags).cuda()
         out = pt.empty(kk, dtype=pt.int64, device="cuda")
         _lib.check(lib.s3_select_topk(_lib.ptr(g), _lib.ptr(f), n, kk, _lib.ptr(out), _lib.stream_ptr()))
-        assert out.cpu().tolist() == ref
+        assert out.cpu().tolist() == ref, (n, k, fused)
+    _lib.check(lib.s3_select_set_fused(1))
 
 
 def test_facade_outputs_and_pickle(cuda, tmp_path):
