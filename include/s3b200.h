@@ -28,6 +28,7 @@ extern "C" {
 
 typedef struct s3_knn s3_knn_t;
 typedef struct s3_geom s3_geom_t;
+typedef struct s3_topo s3_topo_t;
 
 /* ---- library ---------------------------------------------------------------------------------- */
 const char* s3_last_error(void);
@@ -121,6 +122,37 @@ int s3_select_set_fused(int on);
 int s3_build_nodes(const int64_t* d_leaves, int64_t n_leaves, const double* d_center,
                    const int32_t* d_level, const int32_t* d_lattice, int dim, int max_level, double width,
                    int32_t* d_faces, double* d_vertices, int64_t* n_vertices, void* stream);
+
+/* ---- cell topology (HOST side, plain integer bookkeeping; all pointers are host pointers) -----------
+ * The reference's neighbour pointers and shared node ids are history dependent (see csrc/topology.cu); this
+ * handle replays them: Cell.nb / Cell.node_idx / Cell.children of s_cube.py:30-85.
+ *   s3_topo_create        _create_first_cell (s_cube.py:338-397): root cell, its 2^d nodes. async != 0: updates
+ *                         (refine / refresh / mark_invalid) are queued and applied in order by a native worker thread
+ *                         next to the device work; reads wait for the queue, s3_topo_sync reports a queued failure
+ *   s3_topo_refine        per parent, in the given order: _assign_neighbors + _assign_indices
+ *                         (s_cube.py:904-1186, 1188-1536) as called from _refine_cells / _refine_uniform
+ *   s3_topo_refresh       cell.parent.children = _assign_neighbors(cell.parent, children=...) (s_cube.py:611,
+ *                         489-490, 826); of_parents != 0: the list holds the parents (s_cube.py:547-549)
+ *   s3_topo_mark_invalid  neighbour reset of _remove_invalid_cells (s_cube.py:721-731)
+ *   s3_topo_check_nb      _check_nb (s_cube.py:447-464): out int64 [26], returns the count (-1 on bad arguments)
+ *   s3_topo_cell          raw pointers of one cell: nb int32 [8|26], node ids int32 [2^d], {parent, children, level}
+ *                         (children: first child index, -1 = leaf, -2 = removed)
+ *   s3_topo_final         _resort_nodes_and_indices_of_grid + renumber_node_indices_parallel (s_cube.py:734-772,
+ *                         1695-1736): faces int32 [n_leaf, 2^d] in cell-list order, vertices fp64 [n_vertices, dim];
+ *                         call with faces == NULL first to get the sizes; centers_by_index (optional) fp64
+ *                         [n_cells, dim] = the host replay of all cell centres                                  */
+int s3_topo_create(int dim, const double* root_center, double width, int async, s3_topo_t** out);
+int s3_topo_free(s3_topo_t* h);
+int s3_topo_sync(s3_topo_t* h);
+int64_t s3_topo_n_cells(s3_topo_t* h);
+int64_t s3_topo_n_nodes(s3_topo_t* h);
+int s3_topo_refine(s3_topo_t* h, const int64_t* parents, int64_t n);
+int s3_topo_refresh(s3_topo_t* h, const int64_t* cells, int64_t n, int of_parents);
+int s3_topo_mark_invalid(s3_topo_t* h, const int64_t* cells, int64_t n);
+int64_t s3_topo_check_nb(s3_topo_t* h, int64_t cell, int64_t* out);
+int s3_topo_cell(s3_topo_t* h, int64_t cell, int32_t* nb_out, int32_t* node_out, int32_t* state_out);
+int s3_topo_final(s3_topo_t* h, int64_t* n_leaf_out, int64_t* n_vertices_out, int32_t* faces,
+                  double* vertices, double* centers_by_index);
 
 /* sum of metric^2 over the leaves (_compute_captured_metric, s_cube.py:317-336) and of a plain
  * vector (the target norm, s_cube.py:205); d_out fp64 [1]; deterministic reduction tree             */

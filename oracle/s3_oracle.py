@@ -259,13 +259,17 @@ class OracleTree:
     """
     CPU restatement of SamplingTree (s_cube.py:86-902, 1538-1584) on flat Python lists; control flow and the set
     operations that define the cell numbering follow the reference line by line.
-    ``max_delta_level`` (s_cube.py:447-506) is restated geometrically: the neighbour of a cell in a direction is the
-    leaf covering the adjacent same-level lattice position; the reference reaches it through neighbour pointers.
+    ``topology``: optional factory ``(d, root_center, width) -> object`` with the methods of
+    ``oracle.topology_oracle.OracleTopology`` (or the product's ``Topology``); when given, the tree replays the
+    reference's neighbour pointers / node ids (s_cube.py:904-1536) next to the refinement, uses them for the
+    ``max_delta_level`` closure (s_cube.py:447-506, exact) and returns the reference's ``face_ids`` / ``all_nodes``.
+    Without it ``max_delta_level`` is restated geometrically (the neighbour of a cell in a direction is the leaf covering
+    the adjacent same-level lattice position), which equals the pointer version only while no pointer is stale.
     """
 
     def __init__(self, vertices, target, geometries, n_cells=None, uniform_level=5, min_metric=0.75,
                  n_cells_iter_start=None, n_cells_iter_end=None, relTol=1e-3, reach_at_least=0.75, pre_select=False,
-                 sdm_order=1, max_delta_level=False):
+                 sdm_order=1, max_delta_level=False, topology=None):
         self.X = np.ascontiguousarray(vertices, dtype=np.float64)
         self.y = np.ascontiguousarray(target, dtype=np.float64)
         self.geometries = geometries
@@ -310,6 +314,7 @@ class OracleTree:
         self.lattice.append((0,) * self.d); self.lookup[(0,) + (0,) * self.d] = 0
         self.leaf.add(0)
         self.target_norm = float(np.linalg.norm(self.y))
+        self.topo = topology(self.d, c[0].copy(), self.width) if topology is not None else None
 
     def _refine_cells(self, to_refine):
         parents = list(to_refine)
@@ -331,10 +336,14 @@ class OracleTree:
         self.leaf -= all_parents
         self.leaf.update(all_children)
         new = list(range(first, new_index))
+        if self.topo is not None:
+            self.topo.refine(parents)                         # _assign_neighbors + _assign_indices per parent
         self._update_gain(new)
         return new
 
     def _check_nb(self, c):
+        if self.topo is not None:
+            return self.topo.check_nb(c)
         lv, pos, out = self.level[c], self.lattice[c], []
         for dv in self.nb_dirs:
             q = tuple(pos[a] + dv[a] for a in range(self.d))
@@ -354,6 +363,8 @@ class OracleTree:
         while go:
             tmp = set()
             for c in viol:
+                if self.topo is not None:
+                    self.topo.refresh_siblings([c])           # s_cube.py:489-490
                 tmp.update(self._check_nb(c))
             if not tmp or tmp.issubset(viol):
                 go = False
@@ -399,6 +410,8 @@ class OracleTree:
         for c in idx:
             self.invalid[c] = True
             self.gain[c] = 0
+        if self.topo is not None:
+            self.topo.mark_invalid(list(idx))                 # s_cube.py:721-731
         self.leaf -= idx
         return None
 
@@ -428,7 +441,10 @@ class OracleTree:
     def refine(self):
         import heapq
         for _ in range(self.min_level):
+            parents = list(self.leaf)
             new = self._refine_cells(self.leaf)
+            if self.topo is not None:
+                self.topo.refresh_children(parents)           # second pass, s_cube.py:547-549
             self._remove_invalid_cells({c for c in new})
         self.n_after_uniform = len(self.leaf)
         if self.n_cells_max is None:
@@ -443,6 +459,8 @@ class OracleTree:
             to_refine = set()
             for i in srt:
                 to_refine.add(i)
+                if self.topo is not None:
+                    self.topo.refresh_siblings([i])           # s_cube.py:611
                 if self.max_delta_level:
                     to_refine.update(self._check_constraint(set(self._check_nb(i))))
             self._remove_invalid_cells({c for c in self._refine_cells(to_refine)})
@@ -469,6 +487,8 @@ class OracleTree:
                         continue
                     if self.level[i] < hi:
                         to_refine.add(i)
+                        if self.topo is not None:
+                            self.topo.refresh_siblings([i])   # s_cube.py:826
                     if self.max_delta_level:
                         more = set(self._check_nb(i))
                         more.update(self._check_constraint(more))
@@ -485,6 +505,8 @@ class OracleTree:
         self.all_centers = np.stack([self.center[c] for c in order])
         self.all_levels = np.array([self.level[c] for c in order], dtype=np.int64)[:, None]
         self.leaf_order = order
+        if self.topo is not None:
+            self.face_ids, self.all_nodes, _ = self.topo.final()
         return self
 
 

@@ -49,6 +49,17 @@ _SIGNATURES = {
     "s3_select_set_fused": (c_int, [c_int]),
     "s3_build_nodes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p,
                                POINTER(c_int64), c_void_p]),
+    "s3_topo_create": (c_int, [c_int, c_void_p, c_double, c_int, POINTER(c_void_p)]),
+    "s3_topo_sync": (c_int, [c_void_p]),
+    "s3_topo_free": (c_int, [c_void_p]),
+    "s3_topo_n_cells": (c_int64, [c_void_p]),
+    "s3_topo_n_nodes": (c_int64, [c_void_p]),
+    "s3_topo_refine": (c_int, [c_void_p, c_void_p, c_int64]),
+    "s3_topo_refresh": (c_int, [c_void_p, c_void_p, c_int64, c_int]),
+    "s3_topo_mark_invalid": (c_int, [c_void_p, c_void_p, c_int64]),
+    "s3_topo_check_nb": (c_int64, [c_void_p, c_int64, c_void_p]),
+    "s3_topo_cell": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "s3_topo_final": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p, c_void_p]),
     "s3_leaf_sumsq": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "s3_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "s3_interp_gather": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p,

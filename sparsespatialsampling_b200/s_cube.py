@@ -26,6 +26,7 @@ import numpy as np
 import torch as pt
 
 from . import _lib
+from .topology import Topology
 from .knn import KnnIndex, default_n_neighbors
 from .geometry.device import GeometryTable
 
@@ -62,12 +63,21 @@ def probe_sum_order_8() -> int:
 
 
 class SamplingTree(object):
+    # queue the host-side topology replay on the library's worker thread whenever nothing reads it inside the loop
+    topology_async = True
+
     def __init__(self, vertices: pt.Tensor, target: pt.Tensor, geometry_obj: list, n_cells: int = None,
                  uniform_level: int = 5, min_metric: float = 0.75, max_delta_level: bool = False,
                  n_cells_iter_start: int = None, n_cells_iter_end: int = None, n_jobs: int = 1,
                  relTol: Union[int, float] = 1e-3, reach_at_least: float = 0.75, pre_select: bool = False,
-                 device=None, sdm_order: int = None):
+                 device=None, sdm_order: int = None, exact_topology: bool = True):
         _lib.require_cuda()
+        # exact_topology: replay the reference's neighbour pointers / node ids on the host (topology.py) -- the
+        # reference's vertex numbering and max_delta_level closure are history dependent. False: vertices from a
+        # lattice de-duplication on the device and a geometric max_delta_level closure (same cells / centres / levels,
+        # different vertex numbering).
+        self._exact_topology = bool(exact_topology)
+        self._topo = None
         self._lib = _lib.load()
         self._device = pt.device(device) if device is not None else pt.device("cuda", pt.cuda.current_device())
         self._pre_select = pre_select
@@ -103,7 +113,8 @@ class SamplingTree(object):
             self._nb_dirs = ([np.array(p + (0,), dtype=np.int64) for p in plane] +
                              [np.array(p + (-1,), dtype=np.int64) for p in plane + [(0, 0)]] +
                              [np.array(p + (1,), dtype=np.int64) for p in plane + [(0, 0)]])
-        self._cell_lookup = {} if max_delta_level else None       # (level, lattice coords) -> cell index
+        # (level, lattice coords) -> cell index, only for the geometric closure
+        self._cell_lookup = {} if (max_delta_level and not exact_topology) else None
 
         # KNN index over the original grid with the metric as regression target (s_cube.py:161-163)
         t0 = time()
@@ -144,6 +155,11 @@ class SamplingTree(object):
         self._target_norm = float(np.sqrt(self._sumsq(tgt)))
 
     # ------------------------------------------------------------------------------------------ helpers
+    def _topo_call(self, fn, *args) -> None:
+        """Topology update: applied at once with max_delta_level (the closure reads the pointers), otherwise queued on
+        the library's native worker thread and applied next to the device work (Topology(asynchronous=True))."""
+        fn(*args)
+
     def _stream(self):
         return _lib.stream_ptr()
 
@@ -224,6 +240,9 @@ class SamplingTree(object):
         self._leaf_cells.add(0)
         if self._cell_lookup is not None:
             self._cell_lookup[(0,) + (0,) * d] = 0
+        if self._exact_topology:
+            # without max_delta_level nothing reads the pointers before the final grid assembly
+            self._topo = Topology(d, centers_[0].numpy(), self._width, asynchronous=self.topology_async and not self._max_delta_level)
 
     # ------------------------------------------------------------------------------------------ refinement
     def _refine_cells(self, parents: list) -> range:
@@ -245,6 +264,8 @@ class SamplingTree(object):
                                                first, n_new, self._k, self._width, self._gain0, self._sdm_order,
                                                _lib.ptr(self._metric_d), _lib.ptr(self._gain), self._stream()))
         self._levels_h[first:first + n_new] = np.repeat(self._levels_h[par_h] + 1, self._nch)
+        if self._topo is not None and n_par:
+            self._topo_call(self._topo.refine, par_h.copy())   # host replay of _assign_neighbors + _assign_indices
         if self._cell_lookup is not None and n_par:
             # host mirror of the integer lattice position (child = 2 * parent + [direction > 0]) for neighbour look-ups
             d = self._n_dimensions
@@ -280,8 +301,11 @@ class SamplingTree(object):
         """
         Leaf neighbours of a cell (8 / 26 directions, reference order) with a lower level: refining the cell alone would
         create a level difference of two (s_cube.py:447-464). The neighbour in a direction is the leaf covering the
-        adjacent same-level lattice position -- the geometric meaning of the reference's neighbour pointers.
+        adjacent same-level lattice position -- the geometric meaning of the reference's neighbour pointers. With
+        ``exact_topology`` the reference's own (possibly stale) pointers are replayed instead.
         """
+        if self._topo is not None:
+            return self._topo.check_nb(_cell_no)
         lv = int(self._levels_h[_cell_no])
         pos = self._lattice_h[_cell_no]
         out = []
@@ -306,6 +330,8 @@ class SamplingTree(object):
         while new_cells_to_check:
             tmp = set()
             for c in nb_violating_constraint:
+                if self._topo is not None:
+                    self._topo.refresh_siblings([c])          # s_cube.py:489-490
                 tmp.update(self._check_nb(c))
             if not tmp or tmp.issubset(nb_violating_constraint):
                 new_cells_to_check = False
@@ -389,6 +415,8 @@ class SamplingTree(object):
             return _idx
         for c in _idx:
             self._invalid_h[c] = True
+        if self._topo is not None:
+            self._topo_call(self._topo.mark_invalid, list(_idx))   # neighbour reset, s_cube.py:721-731
         self._leaf_cells -= _idx
         return None
 
@@ -398,7 +426,10 @@ class SamplingTree(object):
         self._times["t_start_uniform"] = time()
         for j in range(self._min_level):
             logger.info(f"\r\tStarting iteration no. {j}, N_cells = {len(self._leaf_cells)}")
-            new_cells = self._refine_cells(list(self._leaf_cells))
+            parents = list(self._leaf_cells)
+            new_cells = self._refine_cells(parents)
+            if self._topo is not None:
+                self._topo_call(self._topo.refresh_children, parents)   # second pass, s_cube.py:547-549
             self._current_min_level += 1
             self._remove_invalid_cells(new_cells)
         self._current_max_level = max(self._current_max_level, self._min_level)
@@ -474,9 +505,14 @@ class SamplingTree(object):
             if self._selected_log is not None:
                 self._selected_log.append(list(_leaf_cells_sorted))
             to_refine = set()
+            if self._topo is not None and not self._max_delta_level:
+                # s_cube.py:611 for every selected cell; nothing reads the pointers in between, so one call
+                self._topo_call(self._topo.refresh_siblings, list(_leaf_cells_sorted))
             for i in _leaf_cells_sorted:
                 to_refine.add(i)
                 if self._max_delta_level:
+                    if self._topo is not None:
+                        self._topo.refresh_siblings([i])      # s_cube.py:611
                     nb_to_refine_as_well = set(self._check_nb(i))
                     to_refine.update(self._check_constraint(nb_to_refine_as_well))
             self._remove_invalid_cells(self._refine_cells(list(to_refine)))
@@ -532,17 +568,24 @@ class SamplingTree(object):
 
             while _global_max_level > _global_min_level:
                 logger.info(f"\r\t\t\t\t\t\t\t\t\tRefining level {_global_min_level + 1} / {_global_max_level}.")
-                to_refine, checked = set(), set()
+                to_refine, checked, refresh = set(), set(), []
                 for i in _all_cells:
                     if i in checked:
                         continue
                     if self._levels_h[i] < _global_max_level:
                         to_refine.add(i)
+                        if self._topo is not None:            # s_cube.py:826
+                            if self._max_delta_level:
+                                self._topo.refresh_siblings([i])
+                            else:
+                                refresh.append(i)             # nothing reads the pointers inside this loop
                     if self._max_delta_level:
                         nb_to_refine_as_well = set(self._check_nb(i))
                         nb_to_refine_as_well.update(self._check_constraint(nb_to_refine_as_well))
                         to_refine.update(nb_to_refine_as_well)
                         checked.update(nb_to_refine_as_well)
+                if refresh:
+                    self._topo_call(self._topo.refresh_siblings, refresh)
                 new_cells = self._refine_cells(list(to_refine))
                 _idx_new = {c for c in new_cells}
                 # children are only tested against the geometry being refined (s_cube.py:850)
@@ -572,6 +615,18 @@ class SamplingTree(object):
         n_leaf = len(leaf_order)
         d = self._n_dimensions
         order_d = pt.tensor(leaf_order, dtype=pt.int64, device=self._device)
+        if self._topo is not None:
+            # the reference's node table: shared ids from the replayed pointers, unused ids squeezed out (:750-771)
+            self._topo.sync()
+            faces, vertices, _ = self._topo.final()
+            assert faces.shape[0] == n_leaf, "host topology and device cell state disagree on the leaf cells"
+            self.face_ids = pt.from_numpy(faces)
+            self.all_nodes = pt.from_numpy(vertices)
+            self.all_centers = self._center[order_d].cpu()
+            self.all_levels = self._level[order_d].to(pt.int64).cpu().unsqueeze(-1)
+            self._topo = None                                 # native handle: not part of the pickled object
+            self._times["t_end_renumber"] = time()
+            return
         asc_d = order_d if leaf_order == ascending else pt.tensor(ascending, dtype=pt.int64, device=self._device)
         max_level = int(self._levels_h[np.asarray(ascending, dtype=np.int64)].max())
         faces = pt.empty((n_leaf, self._nch), dtype=pt.int32, device=self._device)

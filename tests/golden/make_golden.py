@@ -94,9 +94,23 @@ def case_definitions(geo):
         geoms=lambda g: [g.CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"]),
                          g.SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"])],
         kwargs=dict(uniform_level=3, min_metric=0.6, n_cells_iter_start=10, max_delta_level=True))
-    # (A 3-D delta-level case is deliberately absent: there the reference's pointer graph goes stale already in the
-    # metric-based loop -- level-4 cells in the wake drag level-2 cells at the far domain boundary into the refinement
-    # set -- so the reference and the geometric restatement differ)
+    # delta-level constraint where the reference's neighbour pointers go stale (a child inherits the same-position child of
+    # a neighbour pointer that still refers to a coarser cell refined later): 3-D metric loop, and 2-D with geometry
+    # refinement. Only the pointer replay (oracle/topology_oracle.py, csrc/topology.cu) reproduces these.
+    x = synth.cylinder3d_cloud(6000, seed=3)
+    cases["g3d_delta"] = dict(
+        coords=x, metric=synth.wake_metric(x, xc=0.8, yc=1.0),
+        geoms=lambda g: [g.CubeGeometry("domain", True, synth.CYL3D["lower"], synth.CYL3D["upper"]),
+                         g.CylinderGeometry3D("cylinder", False, [[0.8, 1.0, 0.0], [0.8, 1.0, zmax]], 0.25)],
+        kwargs=dict(uniform_level=2, min_metric=0.55, n_cells_iter_start=10, max_delta_level=True))
+    x = synth.cylinder2d_cloud(4000, seed=12)
+    cases["g2d_delta_geo"] = dict(
+        coords=x, metric=synth.wake_metric(x),
+        geoms=lambda g: [g.CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"], refine=True,
+                                        min_refinement_level=6),
+                         g.SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"], refine=True,
+                                          min_refinement_level=8)],
+        kwargs=dict(uniform_level=3, min_metric=0.5, n_cells_iter_start=10, max_delta_level=True))
     return cases
 
 
@@ -139,11 +153,57 @@ def run_reference_case(name, case, geo_ref):
     return tree, out
 
 
+def reference_neighbour_table(d: int):
+    """
+    The table behind the reference's hand-written ``_assign_neighbors`` (s_cube.py:904-1186), read off by running it on a
+    parent whose neighbours and their children are labelled dummies: table[c][s] = ("sibling", j) | ("poc", P, j).
+    """
+    from sparseSpatialSampling.s_cube import SamplingTree, Cell
+    nnb, nch = (8, 4) if d == 2 else (26, 8)
+
+    class _Self:
+        _n_dimensions = d
+
+    def make_parent(with_children: bool):
+        nbs = []
+        for P in range(nnb):
+            n = Cell(100 + P, None, nnb * [None], None, 1, dimensions=d)
+            if with_children:
+                n.children = tuple(Cell(1000 + 10 * P + j, n, nnb * [None], None, 2, dimensions=d) for j in range(nch))
+            nbs.append(n)
+        parent = Cell(0, None, nbs, None, 1, dimensions=d)
+        kids = [Cell(1 + j, parent, nnb * [None], None, 2, dimensions=d) for j in range(nch)]
+        return parent, kids
+
+    p1, k1 = make_parent(True)
+    SamplingTree._assign_neighbors(_Self(), p1, children=k1)
+    p0, k0 = make_parent(False)
+    SamplingTree._assign_neighbors(_Self(), p0, children=k0)
+    table = []
+    for c in range(nch):
+        row = []
+        for s_ in range(nnb):
+            a, b = k1[c].nb[s_], k0[c].nb[s_]
+            if 1 <= a.index <= nch:
+                assert b.index == a.index
+                row.append(("sibling", a.index - 1))
+            else:
+                P, j = divmod(a.index - 1000, 10)
+                assert b.index == 100 + P, "parent_or_child must fall back to the same parent neighbour"
+                row.append(("poc", P, j))
+        table.append(row)
+    return table
+
+
 def check_oracle_against_reference(name, case, geo_ref, ref_out):
     from oracle import s3_oracle as orc
+    from oracle.topology_oracle import OracleTopology
     geoms = case["geoms"](geo_ref)
     kw = dict(case["kwargs"])
-    tree = orc.OracleTree(case["coords"].numpy(), case["metric"].numpy(), geoms, **kw, sdm_order=1).refine()
+    tree = orc.OracleTree(case["coords"].numpy(), case["metric"].numpy(), geoms, **kw, sdm_order=1,
+                          topology=OracleTopology).refine()
+    assert np.array_equal(tree.face_ids, ref_out["faces"]), f"{name}: faces (node ids) differ"
+    assert np.array_equal(tree.all_nodes, ref_out["vertices"]), f"{name}: vertices differ"
     assert tree.leaf_order == ref_out["leaf_index"].tolist(), f"{name}: leaf numbering differs"
     assert np.array_equal(tree.all_centers, ref_out["centers"]), f"{name}: centres differ"
     assert np.array_equal(tree.all_levels, ref_out["levels"]), f"{name}: levels differ"
@@ -213,6 +273,10 @@ def main():
     sys.path[:0] = [stubs, REF, ROOT]
     os.environ["PYTHONPATH"] = os.pathsep.join([stubs, REF, ROOT, os.environ.get("PYTHONPATH", "")])
     import sparseSpatialSampling.geometry as geo_ref
+    from oracle.topology_oracle import neighbour_table
+    for d in (2, 3):
+        assert reference_neighbour_table(d) == neighbour_table(d), f"neighbour table differs from the reference ({d}-D)"
+    print("   oracle neighbour table == the reference's _assign_neighbors (4*8 and 8*26 entries)")
     if not [a for a in sys.argv[1:] if not a.startswith("-")]:
         np.savez_compressed(os.path.join(HERE, "geometry_pins.npz"), **geometry_pins(geo_ref))
     cases = case_definitions(geo_ref)

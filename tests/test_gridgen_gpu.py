@@ -2,7 +2,8 @@
 GPU parity of the refinement engine (SamplingTree.refine, s_cube.py:563-667):
   * against golden outputs of the REFERENCE itself (tests/golden/*.npz, made by tests/golden/make_golden.py),
   * against the CPU oracle on inputs that are not in the fixtures.
-Bit-exact: leaf cells (centre bits, level, numbering), N_leaf per iteration, gains and metrics of the leaves.
+Bit-exact: leaf cells (centre bits, level, numbering), N_leaf per iteration, gains and metrics of the leaves, and -- with
+the host-side pointer replay (default) -- the vertex table and the faces (node numbering) of the reference.
 Tolerance: metric_per_iter 1e-12 relative (the reference reduces the norm with torch, a different summation tree).
 """
 import os
@@ -27,7 +28,7 @@ def _run(case, **extra):
     return tree
 
 
-@pytest.mark.parametrize("name", ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta"])
+@pytest.mark.parametrize("name", ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta", "g3d_delta", "g2d_delta_geo"])
 def test_refine_matches_reference_golden(cuda, name):
     import sparsespatialsampling_b200.geometry as geo
     case = case_definitions(geo)[name]
@@ -48,13 +49,26 @@ def test_refine_matches_reference_golden(cuda, name):
     assert np.array_equal(tree._gain[leaves].cpu().numpy(), ref["leaf_gain"])
     assert np.array_equal(tree._metric_d[leaves].cpu().numpy(), ref["leaf_metric"])
     np.testing.assert_allclose(info["metric_per_iter"], ref["metric_per_iter"], rtol=1e-12)
-    # per-cell node coordinates: vertices[faces] within 1e-12 * width of the reference's (vertex numbering differs,
-    # the reference shares nodes by refinement history -- DESIGN.md "node table")
+    # vertex table and faces: identical to the reference's history-dependent node sharing (pointer replay on the host)
+    assert tree.face_ids.dtype == pt.int32
+    assert np.array_equal(tree.face_ids.numpy(), ref["faces"])
+    assert np.array_equal(tree.all_nodes.numpy(), ref["vertices"])
+
+
+@pytest.mark.parametrize("name", ["g2d_metric", "g3d_metric"])
+def test_lattice_vertex_table_variant(cuda, name):
+    # exact_topology=False: vertices from a lattice de-duplication on the device -- same cells, per-cell corner
+    # coordinates within 1e-12 * width of the reference's, different vertex numbering
+    import sparsespatialsampling_b200.geometry as geo
+    case = case_definitions(geo)[name]
+    ref = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    tree = _run(case, exact_topology=False)
+    assert list(tree._leaf_cells) == ref["leaf_index"].tolist()
+    assert np.array_equal(tree.all_centers.numpy(), ref["centers"])
     mine = tree.all_nodes.numpy()[tree.face_ids.numpy().astype(np.int64)]
     theirs = ref["vertices"][ref["faces"].astype(np.int64)]
     assert mine.shape == theirs.shape
     assert np.abs(mine - theirs).max() <= 1e-12 * float(ref["width"])
-    assert tree.face_ids.dtype == pt.int32
     # every vertex is used, no duplicate coordinates in the table
     assert np.unique(tree.face_ids.numpy()).size == tree.all_nodes.shape[0]
 
