@@ -103,6 +103,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def reference_grid_gen(n_cells, grid_info):
+    """The reference's own grid generation on this exact workload, run once in the build container (8 vCPU, n_jobs=8;
+    tests/golden/make_golden_configs.py) -- context for grid_gen_s; tests/test_gridgen_gpu.py checks that the grids are
+    bit-identical."""
+    p = os.path.join(ROOT, "tests", "golden", "config_C2.npz")
+    if not os.path.exists(p) or grid_info is None:
+        return None
+    g = np.load(p)
+    return {"t_total_s": float(g["reference_t_total"]), "n_cells": int(g["n_cells"]), "iterations": int(g["iterations"]),
+            "same_grid": bool(int(g["n_cells"]) == n_cells and int(g["iterations"]) == grid_info["iterations"]),
+            "where": "reference SamplingTree.refine(), build container, 8 vCPU, n_jobs=8 (not the B200 host)",
+            "source": "tests/golden/config_C2.npz"}
+
+
 def algorithmic_bytes(n_unique, n_cells, k, comps, t):
     """unique source rows read once + result written once + the (idx, w) tables."""
     return n_unique * comps * t * 4 + n_cells * comps * t * 4 + n_cells * k * 8
@@ -176,6 +190,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # native libraries (NCCL's version banner) write to fd 1: keep stdout for the one JSON line
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     pt.cuda.set_device(local)
     dev = pt.device("cuda", local)
     if world > 1:
@@ -403,8 +421,11 @@ def run_ours(args):
             "captured_metric": grid_info["metric_per_iter"][-1]},
         "knn_tables_s": t_tables,
         "svd": svd_info,
+        "grid_gen_reference": reference_grid_gen(n_cells, grid_info),
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -184,3 +184,32 @@ def test_input_validation(cuda, tmp_path):
     with pytest.raises(ValueError):
         dom3 = s3.geometry.CubeGeometry("domain", True, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0])
         s3.SparseSpatialSampling(x, pt.rand(100, dtype=pt.float64), [dom3], str(tmp_path), "a")   # dim mismatch
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_full_size_configs_match_the_reference_run(cuda, name):
+    """BASELINE.json configurations C1 (~20k points) and C2 (~100k points, the bench workload) at full size against a run
+    of the reference itself (tests/golden/make_golden_configs.py: SHA-256 of centers / levels / faces / vertices, the
+    per-iteration logs; the reference needed 64 s / 129 s with n_jobs=8 in the build container)."""
+    import hashlib
+    import synth
+    import sparsespatialsampling_b200.geometry as geo
+    from sparsespatialsampling_b200.s_cube import SamplingTree
+    ref = np.load(os.path.join(GOLDEN, f"config_{name}.npz"))
+    x = synth.cylinder2d_cloud(synth.CONFIGS[name][0], seed=0)
+    assert x.shape[0] == int(ref["n_points"])
+    geoms = [geo.CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"]),
+             geo.SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"], refine=True)]
+    tree = SamplingTree(x, synth.wake_metric(x), geoms, uniform_level=5, min_metric=0.75, sdm_order=1)
+    tree.refine()
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    info = tree.data_final_mesh
+    assert info["n_cells"] == int(ref["n_cells"]) and info["iterations"] == int(ref["iterations"])
+    assert info["cells_per_iter"] == ref["cells_per_iter"].tolist()
+    np.testing.assert_allclose(info["metric_per_iter"], ref["metric_per_iter"], rtol=1e-12)
+    assert sha(np.asarray(list(tree._leaf_cells), dtype=np.int64)) == str(ref["leaf_index_sha"])
+    assert sha(tree.all_centers.numpy()) == str(ref["centers_sha"])
+    assert sha(tree.all_levels.numpy()) == str(ref["levels_sha"])
+    assert str(tree.face_ids.numpy().dtype) == str(ref["faces_dtype"])
+    assert sha(tree.face_ids.numpy()) == str(ref["faces_sha"])
+    assert tree.all_nodes.shape[0] == int(ref["n_vertices"]) and sha(tree.all_nodes.numpy()) == str(ref["vertices_sha"])
