@@ -253,6 +253,9 @@ def run_ours(args):
         _lib.check(_lib.load().s3_set_tuning(6, args.prefetch))
     if args.unroll:
         _lib.check(_lib.load().s3_set_tuning(5, args.unroll))
+    for kv in [t for t in args.tune.split(",") if t]:
+        key, val = kv.split("=")
+        _lib.check(_lib.load().s3_set_tuning(int(key), int(val)))
     if args.regs >= 0:
         _lib.check(_lib.load().s3_set_tuning(8, args.regs))
     if args.sync >= 0:
@@ -352,6 +355,8 @@ def run_ours(args):
         g1.record()
         pt.cuda.synchronize()
         svd_ms[method] = g0.elapsed_time(g1) / 3
+    s3svd.compute_svd(a2, area, rank=20)              # first call: one-time cuSOLVER initialisation (~1 s)
+    pt.cuda.synchronize()
     t0 = time.time()
     s_val, _, _ = s3svd.compute_svd(a2, area, rank=20)
     pt.cuda.synchronize()
@@ -443,6 +448,7 @@ def main():
     ap.add_argument("--variant", type=int, default=-1, help="direct kernel: 0 = CTA walks cells, 1 = warp per cell")
     ap.add_argument("--warps", type=int, default=0, help="warp-per-cell kernel: warps (= cells) per CTA")
     ap.add_argument("--unroll", type=int, default=0, help="warp-per-cell kernel: column vectors per lane and step")
+    ap.add_argument("--tune", default="", help="comma separated key=value pairs for s3_set_tuning, e.g. 5=1,9=512")
     ap.add_argument("--regs", type=int, default=-1, help="warp-per-cell kernel: 1 = (idx, w) in registers (k = 8 | 26)")
     ap.add_argument("--sync", type=int, default=-1, help="warp-per-cell kernel: 1 = barrier per column step")
     ap.add_argument("--stage-rows", type=int, default=0, help="pipelined kernel: rows per shared-memory stage")

@@ -12,7 +12,8 @@ from ctypes import c_int, c_int32, c_int64, c_void_p, c_char_p, c_double, POINTE
 import torch as pt
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs3b200.so")
+# S3B200_LIB: alternative build of the same library (A/B measurements of kernel changes)
+LIB_PATH = os.environ.get("S3B200_LIB") or os.path.join(_HERE, "libs3b200.so")
 
 S3_F32 = 0
 S3_F64 = 1

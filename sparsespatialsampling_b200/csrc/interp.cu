@@ -27,6 +27,8 @@ static int g_cells_per_cta = 4;
 static int g_direct_variant = 1;   // 0 = CTA walks cells, 1 = warp per cell (s3_set_tuning key 3)
 static int g_warps_per_cta = 8;
 static int g_direct_regs = 0;      // k = 8 / 26: (idx, w) in registers instead of shuffle broadcasts (s3_set_tuning key 8)
+static int g_direct_window = 1;    // k > 16: window formulation of the warp-per-cell kernel (s3_set_tuning key 12)
+static int g_chunk_cols = 0;       // columns per grid.y window of the warp-per-cell kernel, 0 = by k (s3_set_tuning key 9)
 static int g_direct_sync = 0;      // barrier per column step in the warp-per-cell kernel (s3_set_tuning key 7)
 static int g_unroll = 0;           // column vectors per lane and step (s3_set_tuning key 5)    // warp-per-cell variant (s3_set_tuning key 4)   // tuning knob (s3_set_tuning key 0)
 
@@ -128,11 +130,23 @@ interp_gather_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_
 // (idx, w) of the cell live in registers (lane j holds neighbour j) and are broadcast with shuffles.
 // SYNC: the warps of the CTA additionally meet at a barrier after every column step, so that the row segments shared by
 // neighbouring cells are requested within one step by all warps (L1 hit / hit-under-miss instead of a second fill).
-template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL, bool SYNC>
+// CHUNKED: blockIdx.y selects a window of `chunk_cols` columns (slow grid dimension): all cells sweep window 0, then
+// window 1, ... so that the row segments a wave of CTAs touches (cells in flight x unique rows x window bytes) stay
+// inside the L2 for long rows. The un-chunked instantiation is kept byte for byte: this kernel's speed depends on
+// the load/FMA interleaving ptxas picks for the neighbour loop (an explicit 4-deep batching measured 25 % slower, a
+// different loop bound 10 % slower).
+template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL, bool SYNC, bool CHUNKED>
 __global__ void __launch_bounds__(512)
 interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
                        const Tw* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
-                       Tout* __restrict__ out) {
+                       Tout* __restrict__ out, int64_t row_stride, int64_t chunk_cols) {
+    if (CHUNKED) {
+        // from here on `row_len` is the width of this window; rows are `row_stride` apart
+        const int64_t begin = (int64_t)blockIdx.y * chunk_cols;
+        data += begin;
+        out += begin;
+        row_len = (row_len - begin) < chunk_cols ? (row_len - begin) : chunk_cols;
+    }
     const int warps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t cell = (int64_t)blockIdx.x * warps + warp;
@@ -143,7 +157,7 @@ interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int3
     if (active && lane < k) { idx_lo = idx[cell * k + lane]; w_lo = w[cell * k + lane]; }
     if (active && lane + 32 < k) { idx_hi = idx[cell * k + lane + 32]; w_hi = w[cell * k + lane + 32]; }
     const int64_t orow = !active ? 0 : (out_row ? (int64_t)out_row[cell] : cell);
-    Tout* o = out + orow * row_len;
+    Tout* o = out + orow * (CHUNKED ? row_stride : row_len);
     constexpr int STEP = 32 * V;
     for (int64_t col0 = 0; col0 < row_len; col0 += (int64_t)STEP * UNROLL) {
         if (SYNC) {
@@ -161,7 +175,7 @@ interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int3
         for (int j = 0; j < k; ++j) {
             const int32_t r = __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
             const Tw wj = __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
-            const Tin* src = data + (int64_t)r * row_len + col0 + lane * V;
+            const Tin* src = data + (int64_t)r * (CHUNKED ? row_stride : row_len) + col0 + lane * V;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 if (col0 + u * STEP + lane * V < row_len) {
@@ -178,6 +192,63 @@ interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int3
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t c = col0 + u * STEP + lane * V;
             if (c < row_len) {
+                Vec<Tout, V> ov;
+#pragma unroll
+                for (int e = 0; e < V; ++e) ov.v[e] = (Tout)acc[u][e];
+                *reinterpret_cast<Vec<Tout, V>*>(o + c) = ov;
+            }
+        }
+    }
+}
+
+// Window formulation of the same kernel for the 3-D neighbour count (k = 26): the column range [col_begin, col_end) of
+// blockIdx.y is swept with absolute column indices. Functionally identical to the CHUNKED instantiation above; it exists
+// because ptxas schedules its neighbour loop differently (more loads in flight per warp), which measured 8-10 % faster
+// for k = 26 with two column vectors per lane (C4: 7.0 ms vs 7.8 ms) and 10 % slower for k = 8 with one.
+template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL>
+__global__ void __launch_bounds__(512)
+interp_warpcell_window_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
+                              const Tw* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
+                              Tout* __restrict__ out, int64_t chunk_cols) {
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t cell = (int64_t)blockIdx.x * warps + warp;
+    if (cell >= n_cells) return;
+    const int64_t col_begin = (int64_t)blockIdx.y * chunk_cols;
+    const int64_t col_end = (col_begin + chunk_cols) < row_len ? (col_begin + chunk_cols) : row_len;
+    int32_t idx_lo = 0, idx_hi = 0;
+    Tw w_lo = (Tw)0, w_hi = (Tw)0;
+    if (lane < k) { idx_lo = idx[cell * k + lane]; w_lo = w[cell * k + lane]; }
+    if (lane + 32 < k) { idx_hi = idx[cell * k + lane + 32]; w_hi = w[cell * k + lane + 32]; }
+    const int64_t orow = out_row ? (int64_t)out_row[cell] : cell;
+    Tout* o = out + orow * row_len;
+    constexpr int STEP = 32 * V;
+    for (int64_t col0 = col_begin; col0 < col_end; col0 += (int64_t)STEP * UNROLL) {
+        Tw acc[UNROLL][V];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[u][e] = (Tw)0;
+        for (int j = 0; j < k; ++j) {
+            const int32_t r = __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
+            const Tw wj = __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            const Tin* src = data + (int64_t)r * row_len + col0 + lane * V;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (col0 + u * STEP + lane * V < col_end) {
+                    const Vec<Tin, V> x = ld_stream<Tin, V>(src + u * STEP);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        if (MODE == 0) acc[u][e] = fmaf((float)wj, (float)x.v[e], (float)acc[u][e]);
+                        else acc[u][e] = __dadd_rn((double)acc[u][e], __dmul_rn((double)wj, (double)x.v[e]));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t c = col0 + u * STEP + lane * V;
+            if (c < col_end) {
                 Vec<Tout, V> ov;
 #pragma unroll
                 for (int e = 0; e < V; ++e) ov.v[e] = (Tout)acc[u][e];
@@ -287,16 +358,28 @@ static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, 
             note_launch(1);
             return S3_OK;
         }
-#define S3_WARPCELL(VV, UU, SS)                                                                                 \
-    interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, SS><<<(unsigned)blocks, warps * 32, 0, stream>>>(          \
-        reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p)
+        // column windows (multiple of 256 columns); 0 = none. Measured on C4 (T = 2000, k = 26): windows of 512 / 1024 /
+        // none: 7.32 / 7.41 / 7.27 ms -- the L2 already holds the working set, so windows are off by default
+        int64_t chunk = g_chunk_cols > 0 ? g_chunk_cols : ((int64_t)1 << 40);
+        chunk = ceil_div(chunk, 256) * 256;
+        int64_t n_chunks = ceil_div(row_len, chunk);
+        if (n_chunks > 65535) { chunk = ceil_div(ceil_div(row_len, 65535), 256) * 256; n_chunks = ceil_div(row_len, chunk); }
+        const dim3 wc_grid((unsigned)blocks, (unsigned)n_chunks);
+#define S3_WARPCELL(VV, UU, SS, CC)                                                                             \
+    interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, SS, CC><<<wc_grid, warps * 32, 0, stream>>>(               \
+        reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk)
         const bool sync = g_direct_sync != 0;
-        if (vec_ok && unroll == 2) {
-            if (sync) S3_WARPCELL(VFULL, 2, true); else S3_WARPCELL(VFULL, 2, false);
+        if (k > 16 && vec_ok && unroll == 2 && !sync && g_direct_window != 0) {
+            interp_warpcell_window_kernel<Tin, Tw, Tout, VFULL, MODE, 2><<<wc_grid, warps * 32, 0, stream>>>(
+                reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, chunk);
+        } else if (n_chunks > 1 && vec_ok) {
+            if (unroll == 2) S3_WARPCELL(VFULL, 2, false, true); else S3_WARPCELL(VFULL, 1, false, true);
+        } else if (vec_ok && unroll == 2) {
+            if (sync) S3_WARPCELL(VFULL, 2, true, false); else S3_WARPCELL(VFULL, 2, false, false);
         } else if (vec_ok) {
-            if (sync) S3_WARPCELL(VFULL, 1, true); else S3_WARPCELL(VFULL, 1, false);
+            if (sync) S3_WARPCELL(VFULL, 1, true, false); else S3_WARPCELL(VFULL, 1, false, false);
         } else {
-            S3_WARPCELL(1, 2, false);
+            S3_WARPCELL(1, 2, false, false);
         }
 #undef S3_WARPCELL
         S3_LAUNCH_CHECK();
@@ -368,6 +451,16 @@ extern "C" int s3_set_tuning(int key, int value) {
     if (key == 8) {
         S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: register variant must be 0 or 1");
         s3::g_direct_regs = value;
+        return S3_OK;
+    }
+    if (key == 9) {
+        S3_REQUIRE(value >= 0, "s3_set_tuning: window columns must be >= 0");
+        s3::g_chunk_cols = value;
+        return S3_OK;
+    }
+    if (key == 12) {
+        S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: window formulation must be 0 or 1");
+        s3::g_direct_window = value;
         return S3_OK;
     }
     if (key == 10) {
