@@ -1,0 +1,35 @@
+"""
+BASELINE.json configurations C3, C4 and C5 at their full point counts (1 M points 2-D; 10 M points 3-D; 10 M points with an
+STL body + weighted SVD) through size-independent properties -- no reference run is possible at these sizes in a test:
+grid consistency (lattice positions, no duplicate leaves, corner coordinates, faces/vertices), geometry masks of a cell
+sample against the CPU oracle, KNN indices / weights of a cell sample against the oracle's brute-force search (bit-exact
+indices), interpolation tolerance on that sample, reproduction of a constant field, linearity, and for C5 the Gram matrix
+against an fp64 contraction, singular values against its eigenvalues, orthonormality of the weighted modes.
+The checks live in scripts/run_config.py (which is also the script behind profiles/r1_config*.json); the snapshot count
+is reduced for the 3-D cases (the properties do not depend on T, the full T = 2000 runs are in profiles/).
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name,extra", [("C3", []), ("C4", ["--snapshots", "64"]), ("C5", ["--snapshots", "64"])])
+def test_full_size_configuration(cuda, name, extra):
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_config.py"), name] + extra,
+                          capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    line = json.loads(proc.stdout.strip().splitlines()[-1])
+    assert line["config"] == name and line["checks"].endswith(": ok")
+    assert line["n_points"] > (9e5 if name == "C3" else 9e6)
+    assert line["n_cells"] > 1e5 and line["grid_gen_s"] < 30.0
+    assert line["k"] == (8 if name == "C3" else 26)
+    if name == "C5":
+        svd = line["svd"]
+        assert svd["gram_max_rel_err_vs_fp64"] <= 5e-6 and svd["s_rel_err_top"] <= 1e-4
+        assert svd["mode_orthonormality_err"] <= 1e-3
