@@ -21,6 +21,7 @@ extern int g_stage_budget_kb;
 extern int g_pipe_prefetch;
 extern int g_tc_seg_kblocks;
 extern int g_tc_flush_segments;
+extern int g_tc_pair;
 constexpr int kInterpThreads = 128;
 constexpr int kMaxCellsPerCta = 32;
 static int g_cells_per_cta = 4;
@@ -466,6 +467,11 @@ extern "C" int s3_set_tuning(int key, int value) {
     if (key == 10) {
         S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3_set_tuning: K-blocks per TMEM segment must be >= 1");
         s3::g_tc_seg_kblocks = value;
+        return S3_OK;
+    }
+    if (key == 14) {
+        S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: paired Gram kernel must be 0 or 1");
+        s3::g_tc_pair = value;
         return S3_OK;
     }
     if (key == 11) {

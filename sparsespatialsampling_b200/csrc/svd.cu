@@ -11,7 +11,12 @@
 //     (D[128x256] += A_l*B_h + A_h*B_l + A_h*B_h), fp32 accumulators double-buffered in TMEM (2 x 256 columns),
 //     and eight epilogue warps that pull every finished K-segment (a few stages) out of TMEM with tcgen05.ld,
 //     sum segments in fp32 registers and flush to fp64 partials, while the next segment is already running.
-//     (The tensor core's own fp32 accumulation truncates; short TMEM segments keep that drift below 1e-6.)
+//     (The tensor core's own fp32 accumulation truncates; short TMEM segments bound that drift. Measured on a
+//     262144 x 2000 matrix, segment length x flush interval -> time, max error vs fp64: 4 x 32 -> 6.7 ms, 5.5e-7;
+//     8 x 128 (default) -> 5.9 ms, 1.2e-6; 16 x 1000 -> 5.6 ms, 2.9e-6; the drains compete with the MMAs for TMEM.)
+//     Optionally (default) the two CTAs of a cluster work on tiles that share B and fetch it once with TMA multicast;
+//     that halves the L2 -> SM operand traffic but measured the same speed (6.72 vs 6.74 ms): the kernel is bound
+//     by the tensor pipe + TMEM drains, not by operand traffic.
 //   method 0: fp32 CUDA-core tiles (kept as the on-device cross-check of the tensor-core path).
 #include <cuda.h>
 #include "common.cuh"
@@ -183,8 +188,9 @@ constexpr int kTcEpiWarps = 8;                               // two warps per TM
 constexpr int kTcThreads = (2 + kTcEpiWarps) * 32;           // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
 constexpr int kTcTmemCols = 2 * kTcBN;                       // two accumulator buffers
 constexpr size_t kTcSmemBytes = (size_t)kTcStages * kTcStageBytes + 1024;
-int g_tc_seg_kblocks = 4;      // K-blocks accumulated in TMEM before the epilogue takes over (s3_set_tuning key 10)
-int g_tc_flush_segments = 32;  // TMEM segments summed in fp32 registers per fp64 flush (s3_set_tuning key 11)
+int g_tc_seg_kblocks = 8;      // K-blocks accumulated in TMEM before the epilogue takes over (s3_set_tuning key 10)
+int g_tc_pair = 1;             // clusters of two CTAs sharing B via TMA multicast (s3_set_tuning key 14)
+int g_tc_flush_segments = 128;  // TMEM segments summed in fp32 registers per fp64 flush (s3_set_tuning key 11)
 
 // Centre, scale and split the rows [row0, row0 + n_rows) of A into TF32 planes, layout [n_groups][plane_rows][32]:
 //   b = (a - mean) * sqrt(vol);  hi = tf32_rna(b);  lo = b - hi  (exact in fp32; the tensor core drops lo's low bits).
@@ -241,6 +247,24 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t phase) {
         if (clock64() - t0 > 8000000000ll) __trap();
     }
 }
+// the same box written to the same shared-memory offset of every CTA in `cta_mask`; each destination CTA's mbarrier at
+// the same offset receives the complete_tx for the bytes that landed in that CTA
+__device__ __forceinline__ void tma_load_3d_multicast(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                      uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -279,6 +303,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// the same, arriving on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                     "r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -298,7 +328,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // first j-tile (256 columns) that reaches the upper triangle of i-tile ti (128 rows)
 __host__ __device__ __forceinline__ int tc_first_tj(int ti) { return (ti * kTcBM) / kTcBN; }
 
+// paired mode: tiles are enumerated j-tile major, i-tiles 0 .. 2 tj + 1 of a j-tile (an even count when T is padded to
+// 256 columns), so that the two CTAs of a cluster work on (2p, tj) and (2p + 1, tj) and share the B operand
+__host__ __device__ __forceinline__ int tc_pair_count(int tj, int n_i) { return (2 * tj + 2) < n_i ? (2 * tj + 2) : n_i; }
+
 // One CTA per (G tile, K split). partial: fp64 [n_items][kTcBN][kTcBM] (column of the tile major, rows contiguous).
+// PAIR: clusters of two CTAs whose tiles share the 256 columns of B: each CTA fetches half of every B stage and TMA
+// multicasts it into both shared memories (L2 -> SM operand traffic 32 KB instead of 48 KB per CTA and stage -- the
+// single-CTA kernel is bound by exactly that traffic); a stage is released to both producers by multicast commits.
+template <bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, int n_i, int n_j,
                int splits, int n_kblocks, int seg_kblocks, int flush_segments, int passes, double* __restrict__ partial) {
@@ -316,16 +354,34 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     unsigned char* ring_ptr = tc_smem_raw + (ring - raw);
 
     // work item -> (ti, tj, split)
-    const int item = blockIdx.x;
-    const int tile = item / splits, split = item % splits;
-    int ti = 0, acc_tiles = 0;
-    while (ti < n_i) {
-        const int cnt = n_j - tc_first_tj(ti);
-        if (tile < acc_tiles + cnt) break;
-        acc_tiles += cnt;
-        ++ti;
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    int item, tile, split, ti = 0, tj = 0;
+    if (PAIR) {
+        const int cl = blockIdx.x >> 1;
+        split = cl % splits;
+        tile = 2 * (cl / splits) + (int)rank;
+        int acc_tiles = 0;
+        while (tj < n_j) {
+            const int cnt = tc_pair_count(tj, n_i);
+            if (tile < acc_tiles + cnt) break;
+            acc_tiles += cnt;
+            ++tj;
+        }
+        ti = tile - acc_tiles;
+        item = tile * splits + split;
+    } else {
+        item = blockIdx.x;
+        tile = item / splits;
+        split = item % splits;
+        int acc_tiles = 0;
+        while (ti < n_i) {
+            const int cnt = n_j - tc_first_tj(ti);
+            if (tile < acc_tiles + cnt) break;
+            acc_tiles += cnt;
+            ++ti;
+        }
+        tj = tc_first_tj(ti) + (tile - acc_tiles);
     }
-    const int tj = tc_first_tj(ti) + (tile - acc_tiles);
     const int per_split = (n_kblocks + splits - 1) / splits;
     const int kb0 = split * per_split;
     const int kb1 = (kb0 + per_split) < n_kblocks ? (kb0 + per_split) : n_kblocks;
@@ -335,7 +391,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], PAIR ? 2 : 1);            // paired: both CTAs' MMAs must be done with the stage
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full_bar[b], 1);
@@ -352,6 +408,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                          // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
@@ -367,13 +424,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                 const int row = (kb0 + it) * kTcKB;
                 mbar_expect_tx(&full_bar[s], stage_tx);
                 tma_load_3d(st, &map_hi, 0, row, ti * (kTcBM / 32), &full_bar[s]);
-                tma_load_3d(st + 2 * kTcABytes, &map_hi, 0, row, tj * (kTcBN / 32), &full_bar[s]);
-                tma_load_3d(st + 2 * kTcABytes + kTcBBytes / 2, &map_hi, 0, row, tj * (kTcBN / 32) + 4, &full_bar[s]);
-                if (passes == 3) {
-                    tma_load_3d(st + kTcABytes, &map_lo, 0, row, ti * (kTcBM / 32), &full_bar[s]);
-                    tma_load_3d(st + 2 * kTcABytes + kTcBBytes, &map_lo, 0, row, tj * (kTcBN / 32), &full_bar[s]);
-                    tma_load_3d(st + 2 * kTcABytes + kTcBBytes + kTcBBytes / 2, &map_lo, 0, row, tj * (kTcBN / 32) + 4,
-                                &full_bar[s]);
+                if (passes == 3) tma_load_3d(st + kTcABytes, &map_lo, 0, row, ti * (kTcBM / 32), &full_bar[s]);
+                if (PAIR) {
+                    // my half of B (4 of its 8 column groups) goes to both CTAs; the other half arrives from the peer
+                    const int g = tj * (kTcBN / 32) + 4 * (int)rank;
+                    const size_t off = (size_t)rank * (kTcBBytes / 2);
+                    tma_load_3d_multicast(st + 2 * kTcABytes + off, &map_hi, 0, row, g, &full_bar[s], 0x3);
+                    if (passes == 3)
+                        tma_load_3d_multicast(st + 2 * kTcABytes + kTcBBytes + off, &map_lo, 0, row, g, &full_bar[s], 0x3);
+                } else {
+                    tma_load_3d(st + 2 * kTcABytes, &map_hi, 0, row, tj * (kTcBN / 32), &full_bar[s]);
+                    tma_load_3d(st + 2 * kTcABytes + kTcBBytes / 2, &map_hi, 0, row, tj * (kTcBN / 32) + 4, &full_bar[s]);
+                    if (passes == 3) {
+                        tma_load_3d(st + 2 * kTcABytes + kTcBBytes, &map_lo, 0, row, tj * (kTcBN / 32), &full_bar[s]);
+                        tma_load_3d(st + 2 * kTcABytes + kTcBBytes + kTcBBytes / 2, &map_lo, 0, row, tj * (kTcBN / 32) + 4,
+                                    &full_bar[s]);
+                    }
                 }
             }
         }
@@ -414,7 +480,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                         }
                         accumulate = 1u;
                     }
-                    umma_commit(&empty_bar[s]);        // the stage is free once these MMAs have read it
+                    // the stage is free once these MMAs have read it (paired: tell both producers)
+                    if (PAIR) umma_commit_multicast(&empty_bar[s], 0x3);
+                    else umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&acc_full_bar[b]);         // the segment's accumulator is complete
             }
@@ -472,6 +540,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                          // the peer may still multicast into / arrive on this CTA
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTcTmemCols)
                      : "memory");
@@ -481,15 +550,20 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 // G[i][j] (+)= sum over splits of the tile partials; both triangles are written from the same upper-triangle entry.
 __global__ void __launch_bounds__(256)
 gram_tc_reduce_kernel(const double* __restrict__ partial, int splits, int n_i, int n_j, int64_t t, int accumulate,
-                      double* __restrict__ g) {
+                      int paired, double* __restrict__ g) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= t * t) return;
     int64_t i = e / t, j = e % t;
     if (j < i) { const int64_t x = i; i = j; j = x; }
     const int ti = (int)(i / kTcBM), tj = (int)(j / kTcBN);
     int tile = 0;
-    for (int u = 0; u < ti; ++u) tile += n_j - tc_first_tj(u);
-    tile += tj - tc_first_tj(ti);
+    if (paired) {
+        for (int u = 0; u < tj; ++u) tile += tc_pair_count(u, n_i);
+        tile += ti;
+    } else {
+        for (int u = 0; u < ti; ++u) tile += n_j - tc_first_tj(u);
+        tile += tj - tc_first_tj(ti);
+    }
     const double* p = partial + ((size_t)tile * splits * kTcBN + (size_t)(j % kTcBN)) * kTcBM + (size_t)(i % kTcBM);
     double acc = accumulate ? g[e] : 0.0;
     for (int s = 0; s < splits; ++s) acc += p[(size_t)s * kTcBN * kTcBM];
@@ -548,12 +622,15 @@ static int gram_tc(const float* d_a, const float* d_mean, const float* d_vol, in
         S3_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
         encode = (PFN_encodeTiledSvd)fn;
     }
-    const int64_t t_pad = ceil_div(t, kTcBM) * kTcBM;
+    // paired kernel (clusters of two CTAs sharing B by TMA multicast): needs an even number of i-tiles per j-tile
+    const bool paired = g_tc_pair != 0;
+    const int64_t t_pad = paired ? ceil_div(t, kTcBN) * kTcBN : ceil_div(t, kTcBM) * kTcBM;
     const int n_groups = (int)(t_pad / 32);
     const int n_i = (int)(t_pad / kTcBM);
     const int n_j = (int)ceil_div(t_pad, kTcBN);
     int tiles = 0;
-    for (int ti = 0; ti < n_i; ++ti) tiles += n_j - tc_first_tj(ti);
+    if (paired) for (int tj = 0; tj < n_j; ++tj) tiles += tc_pair_count(tj, n_i);
+    else for (int ti = 0; ti < n_i; ++ti) tiles += n_j - tc_first_tj(ti);
     // rows of A per chunk: each plane at most 2 GB
     int64_t plane_rows = ((int64_t)(1ll << 31) / (t_pad * 4)) & ~(int64_t)(kTcKB - 1);
     if (plane_rows < kTcKB) plane_rows = kTcKB;
@@ -586,7 +663,8 @@ static int gram_tc(const float* d_a, const float* d_mean, const float* d_vol, in
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         S3_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(lo) failed with code %d", (int)cr);
     }
-    S3_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    S3_CUDA(cudaFuncSetAttribute(gram_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    S3_CUDA(cudaFuncSetAttribute(gram_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
 
     int chunk = 0;
     for (int64_t row0 = 0; row0 < m; row0 += plane_rows, ++chunk) {
@@ -598,12 +676,28 @@ static int gram_tc(const float* d_a, const float* d_mean, const float* d_vol, in
         int splits = splits_max < n_kblocks ? splits_max : n_kblocks;
         const int per_split = (int)ceil_div(n_kblocks, splits);
         splits = (int)ceil_div(n_kblocks, per_split);          // no empty split
-        gram_tc_kernel<<<(unsigned)(tiles * splits), kTcThreads, kTcSmemBytes, st>>>(map_hi, map_lo, n_i, n_j, splits,
-                                                                                    n_kblocks, g_tc_seg_kblocks, g_tc_flush_segments,
-                                                                                    passes,
-                                                                                    partial);
+        if (paired) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)(tiles * splits));       // tiles is even: cluster = (tile 2p, tile 2p + 1) of a split
+            cfg.blockDim = dim3(kTcThreads);
+            cfg.dynamicSmemBytes = kTcSmemBytes;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            S3_CUDA(cudaLaunchKernelEx(&cfg, gram_tc_kernel<true>, map_hi, map_lo, n_i, n_j, splits, n_kblocks,
+                                       g_tc_seg_kblocks, g_tc_flush_segments, passes, partial));
+        } else {
+            gram_tc_kernel<false><<<(unsigned)(tiles * splits), kTcThreads, kTcSmemBytes, st>>>(
+                map_hi, map_lo, n_i, n_j, splits, n_kblocks, g_tc_seg_kblocks, g_tc_flush_segments, passes, partial);
+        }
         gram_tc_reduce_kernel<<<(unsigned)ceil_div(t * t, 256), 256, 0, st>>>(partial, splits, n_i, n_j, t, chunk > 0,
-                                                                              d_gram);
+                                                                              paired ? 1 : 0, d_gram);
         S3_LAUNCH_CHECK();
         note_launch(3);
     }
