@@ -94,6 +94,40 @@ __device__ __forceinline__ double rdist_box(const double* q, const double* lo, c
     return r;
 }
 
+// (d, i) lexicographic "a before b"
+__device__ __forceinline__ bool topk_less(double ad, int32_t ai, double bd, int32_t bi) {
+    return (ad < bd) || (ad == bd && ai < bi);
+}
+
+// compare-exchange step of a warp-wide bitonic network on (d, i) pairs: partner lane ^ j, the lower lane of the pair
+// keeps the smaller element iff `ascending`
+__device__ __forceinline__ void topk_cmpx(double& d, int32_t& i, int j, bool ascending) {
+    const double od = shfl_xor_d(d, j);
+    const int32_t oi = __shfl_xor_sync(0xffffffffu, i, j);
+    const bool lower = ((threadIdx.x & 31) & j) == 0;
+    const bool other_first = topk_less(od, oi, d, i);
+    // keep the minimum when (lower lane, ascending) or (upper lane, descending)
+    const bool keep_min = (lower == ascending);
+    if (keep_min ? other_first : topk_less(d, i, od, oi)) { d = od; i = oi; }
+}
+
+// Merge the 32 candidates held one per lane (non-candidates = (+inf, INT_MAX)) into the sorted best list: bitonic sort
+// of the candidates, then min(best[l], cand[31-l]) is a bitonic sequence holding the 32 smallest of the union, which
+// one bitonic merge sorts again. ~210 instructions whatever the number of candidates; the one-at-a-time insertion
+// costs ~27 per candidate, so this path is taken when 8 or more points of a leaf beat the current k-th distance.
+__device__ __forceinline__ void topk_merge_sorted(WarpTopK& best, double cd, int32_t ci) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) topk_cmpx(cd, ci, j, (lane & k2) == 0);
+    const double rd = shfl_d(cd, 31 - lane);
+    const int32_t ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+    if (topk_less(rd, ri, best.d, best.i)) { best.d = rd; best.i = ri; }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) topk_cmpx(best.d, best.i, j, true);
+}
+
 // One warp searches the k nearest neighbours of q. On return lane j (< k) holds the j-th neighbour
 // (ascending reduced distance, ties by original index). `stack_*` is per-warp shared memory.
 template <int DIM>
@@ -137,6 +171,14 @@ __device__ __forceinline__ WarpTopK warp_knn_search(const KnnView& ix, const dou
             const double rd = rdist_point<DIM>(q, x, y, z);
             bool pass = valid && (rd < kth_d || (rd == kth_d && oi < kth_i));
             uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (__popc(m) >= 8) {
+                // many points of this leaf beat the current k-th distance (always true for the first leaves, while the
+                // list is still filling): merge them in one sorting-network pass
+                topk_merge_sorted(best, pass ? rd : __longlong_as_double(0x7ff0000000000000ll), pass ? oi : 0x7fffffff);
+                kth_d = shfl_d(best.d, k - 1);
+                kth_i = __shfl_sync(0xffffffffu, best.i, k - 1);
+                m = 0;
+            }
             while (m) {
                 const int src = __ffs(m) - 1;
                 const double cd = shfl_d(rd, src);
