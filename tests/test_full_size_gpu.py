@@ -5,7 +5,7 @@ grid consistency (lattice positions, no duplicate leaves, corner coordinates, fa
 sample against the CPU oracle, KNN indices / weights of a cell sample against the oracle's brute-force search (bit-exact
 indices), interpolation tolerance on that sample, reproduction of a constant field, linearity, and for C5 the Gram matrix
 against an fp64 contraction, singular values against its eigenvalues, orthonormality of the weighted modes.
-The checks live in scripts/run_config.py (which is also the script behind profiles/r1_config*.json); the snapshot count
+The checks live in scripts/run_config.py (which is also the script behind profiles/r1_configs_c3_c4_c5.jsonl); the snapshot count
 is reduced for the 3-D cases (the properties do not depend on T, the full T = 2000 runs are in profiles/).
 """
 import json
