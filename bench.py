@@ -206,15 +206,20 @@ def run_ours(args):
     k = 8
 
     # ---- grid generation on rank 0 (replicas only: the loop is sequential), then broadcast grid + tables
-    grid_info, t_grid_wall = None, None
+    grid_info, t_grid_wall, grid_cold = None, None, None
     if rank == 0:
-        t0 = time.time()
-        sc = s3.SparseSpatialSampling(x, metric, geometries(s3.geometry), "/tmp/s3b200_bench", "c2", **{
-            "uniform_levels": GRID_KW["uniform_level"], "min_metric": GRID_KW["min_metric"]})
-        sc.execute_grid_generation()
-        pt.cuda.synchronize()
-        t_grid_wall = time.time() - t0
-        grid_info = sc.mesh_info
+        # two runs: the first pays one-off costs of the process (module load, first cooperative launch, memory pools),
+        # the second is the steady-state number reported as grid_gen_s; both produce the same grid
+        for attempt in range(2):
+            t0 = time.time()
+            sc = s3.SparseSpatialSampling(x, metric, geometries(s3.geometry), "/tmp/s3b200_bench", "c2", **{
+                "uniform_levels": GRID_KW["uniform_level"], "min_metric": GRID_KW["min_metric"]})
+            sc.execute_grid_generation()
+            pt.cuda.synchronize()
+            t_grid_wall = time.time() - t0
+            grid_info = sc.mesh_info
+            if attempt == 0:
+                grid_cold = {"t_total": grid_info["t_total"], "wall_incl_setup_s": t_grid_wall}
         centers = sc.centers.to(dev)
     else:
         sc, centers = None, None
@@ -423,7 +428,7 @@ def run_ours(args):
             "t_geometry": grid_info["t_geometry"], "t_renumbering": grid_info["t_renumbering"],
             "t_knn_build": grid_info["t_knn_build"], "wall_incl_setup_s": t_grid_wall,
             "iterations": grid_info["iterations"], "n_cells": grid_info["n_cells"],
-            "captured_metric": grid_info["metric_per_iter"][-1]},
+            "captured_metric": grid_info["metric_per_iter"][-1], "first_run_in_process": grid_cold},
         "knn_tables_s": t_tables,
         "svd": svd_info,
         "grid_gen_reference": reference_grid_gen(n_cells, grid_info),

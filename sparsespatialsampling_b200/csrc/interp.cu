@@ -486,6 +486,8 @@ extern "C" int s3_set_tuning(int key, int value) {
 extern "C" int s3_interp_gather(const void* d_data, int data_dtype, int64_t n_src, int64_t row_len,
                                 const int32_t* d_idx, const void* d_w, int64_t n_cells, int k,
                                 const int32_t* d_out_row, void* d_out, int out_dtype, void* stream) {
+    S3_REQUIRE(n_cells >= 0 && row_len >= 0, "s3_interp_gather: bad sizes");
+    if (n_cells == 0 || row_len == 0) return S3_OK;          // empty grids / empty rows: nothing to do (buffers may be NULL)
     S3_REQUIRE(d_data && d_idx && d_w && d_out, "s3_interp_gather: NULL argument");
     S3_REQUIRE(k >= 1 && k <= 64, "s3_interp_gather: k=%d out of range", k);
     S3_REQUIRE(n_src >= 1 && row_len >= 0 && n_cells >= 0, "s3_interp_gather: bad sizes");

@@ -325,27 +325,33 @@ int s3_knn_free(s3_knn_t* h) {
 
 int s3_knn_query(const s3_knn_t* h, const double* d_query, int64_t nq, int k, int64_t* d_idx, double* d_dist,
                  void* stream) {
-    S3_REQUIRE(h && d_query && d_idx && d_dist, "s3_knn_query: NULL argument");
+    S3_REQUIRE(h && nq >= 0, "s3_knn_query: NULL handle or negative query count");
+    if (nq == 0) return S3_OK;                               // no queries: the (empty) buffers may be NULL
+    S3_REQUIRE(d_query && d_idx && d_dist, "s3_knn_query: NULL argument");
     return launch_query<0>(h->ix, d_query, nq, k, d_idx, d_dist, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int s3_knn_predict(const s3_knn_t* h, const double* d_query, int64_t nq, int k, double* d_pred, void* stream) {
-    S3_REQUIRE(h && d_query && d_pred, "s3_knn_predict: NULL argument");
+    S3_REQUIRE(h && nq >= 0, "s3_knn_predict: NULL handle or negative query count");
+    if (nq == 0) return S3_OK;
+    S3_REQUIRE(d_query && d_pred, "s3_knn_predict: NULL argument");
     S3_REQUIRE(h->ix.values != nullptr, "s3_knn_predict: index was built without values");
     return launch_query<1>(h->ix, d_query, nq, k, nullptr, nullptr, d_pred, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int s3_knn_tables(const s3_knn_t* h, const double* d_query, int64_t nq, int k, int32_t* d_idx, float* d_w32,
                   double* d_w64, void* stream) {
-    S3_REQUIRE(h && d_query && d_idx && d_w32, "s3_knn_tables: NULL argument");
+    S3_REQUIRE(h && nq >= 0, "s3_knn_tables: NULL handle or negative query count");
+    if (nq == 0) return S3_OK;
+    S3_REQUIRE(d_query && d_idx && d_w32, "s3_knn_tables: NULL argument");
     return launch_query<2>(h->ix, d_query, nq, k, nullptr, nullptr, nullptr, d_idx, d_w32, d_w64, (cudaStream_t)stream);
 }
 
 int s3_morton_order(const double* d_coords, int64_t n, int dim, int32_t* d_perm, void* stream) {
-    S3_REQUIRE(d_coords && d_perm, "s3_morton_order: NULL argument");
     S3_REQUIRE(dim == 2 || dim == 3, "s3_morton_order: dim must be 2 or 3");
     S3_REQUIRE(n >= 0 && n < ((int64_t)1 << 31), "s3_morton_order: n out of range");
     if (n == 0) return S3_OK;
+    S3_REQUIRE(d_coords && d_perm, "s3_morton_order: NULL argument");
     cudaStream_t st_ = (cudaStream_t)stream;
     Scratch scratch(st_);
     const int nparts = (int)(ceil_div(n, 256) < 1024 ? ceil_div(n, 256) : 1024);
