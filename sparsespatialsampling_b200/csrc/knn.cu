@@ -214,7 +214,8 @@ static int knn_build_impl(const double* coords, int64_t n, int dim, const double
     ix->dim = dim;
     ix->n = n;
     ix->n_pad = ceil_div(n, kKnnFan) * kKnnFan;
-    // level sizes
+    // level sizes (the search encodes a node index in 24 bits of a stack entry: at most 2^24 leaves = 5.4e8 points)
+    S3_REQUIRE(ix->n_pad / kKnnFan < ((int64_t)1 << 24), "s3_knn_build: more than 2^24 leaves (%lld points)", (long long)n);
     int64_t cnt = ix->n_pad / kKnnFan, off = 0;
     int L = 0;
     while (true) {

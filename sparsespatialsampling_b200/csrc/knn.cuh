@@ -141,9 +141,10 @@ __device__ __forceinline__ WarpTopK warp_knn_search(const KnnView& ix, const dou
     int32_t kth_i = best.i;
 
     int sp = 0;
+    // stack entry: level (3 bits) | number of entries of the same push group below this one (5 bits) | node (24 bits)
     if (lane == 0) {
         stack_lb[0] = 0.0;
-        stack_node[0] = (int32_t)(((uint32_t)(ix.n_levels - 1) << 27) | 0u);
+        stack_node[0] = (int32_t)(((uint32_t)(ix.n_levels - 1) << 29) | 0u);
     }
     sp = 1;
     __syncwarp();
@@ -153,9 +154,14 @@ __device__ __forceinline__ WarpTopK warp_knn_search(const KnnView& ix, const dou
         const double lb = stack_lb[sp];
         const uint32_t enc = (uint32_t)stack_node[sp];
         __syncwarp();
-        if (lb > kth_d) continue;
-        const int level = (int)(enc >> 27);
-        const int64_t node = (int64_t)(enc & 0x07ffffffu);
+        if (lb > kth_d) {
+            // the children of a node were pushed nearest-on-top: everything of this group still below has a larger
+            // bound and is pruned as well
+            sp -= (int)((enc >> 24) & 31u);
+            continue;
+        }
+        const int level = (int)(enc >> 29);
+        const int64_t node = (int64_t)(enc & 0x00ffffffu);
         if (level == 0) {
             // leaf: 32 consecutive sorted points, one per lane
             const int64_t p = node * kKnnFan + lane;
@@ -224,9 +230,9 @@ __device__ __forceinline__ WarpTopK warp_knn_search(const KnnView& ix, const dou
                 rank += (v < clb || (v == clb && j < lane)) ? 1 : 0;
             }
             if (push) {
-                const int slot = sp + (npush - 1 - rank);  // nearest child ends on top
-                stack_lb[slot] = clb;
-                stack_node[slot] = (int32_t)(((uint32_t)clevel << 27) | (uint32_t)child);
+                const int below = npush - 1 - rank;        // nearest child ends on top
+                stack_lb[sp + below] = clb;
+                stack_node[sp + below] = (int32_t)(((uint32_t)clevel << 29) | ((uint32_t)below << 24) | (uint32_t)child);
             }
             sp += npush;
             __syncwarp();
