@@ -204,6 +204,11 @@ int s3_interp_pipelined(const float* d_data, int64_t n_src, int64_t row_len, con
  * (`kind` 0 = host to device, 1 = device to host; pinned host memory), `width`/pitches in bytes.            */
 int s3_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
                     int64_t height, int kind, void* stream);
+/* the window [0, width) (fp32 elements) of the rows d_rows[0..n_rows) of a pitched fp32 matrix `src` into the dense
+ * buffer d_dst [n_rows, dst_pitch]. `src` may be PINNED HOST memory (the kernel reads it over PCIe): only the source
+ * rows the sampled grid references cross the bus. Pitches in elements; n_ctas = 0: two CTAs per SM.              */
+int s3_gather_rows(const float* src, int64_t src_pitch, const int32_t* d_rows, int64_t n_rows, int64_t width,
+                   float* d_dst, int64_t dst_pitch, int n_ctas, void* stream);
 
 /* ---- volume-weighted snapshot SVD ---------------------------------------------------------------
  * device side of compute_svd (sparseSpatialSampling/utils.py:302-346), method of snapshots:

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "s3_interp_pipelined": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                     c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "s3_copy2d_async": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "s3_gather_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "s3_svd_row_means": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "s3_svd_gram": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "s3_svd_project": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),

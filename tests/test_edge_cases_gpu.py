@@ -81,7 +81,9 @@ def test_svd_of_tiny_and_single_snapshot_matrices(cuda):
         ref = ref.T @ ref
         for method in ("tc3", "tc", "simt"):
             g = svd.gram(a, mean, vol, 1, method)
-            assert pt.allclose(g, ref, rtol=1e-3, atol=1e-5 * float(ref.abs().max() + 1e-30) + 1e-12), (m, t, method)
+            # single-pass TF32 ("tc") rounds the inputs to 11 bits: 3e-3 of the largest entry; the others 1e-5
+            atol = (3e-3 if method == "tc" else 1e-5) * float(ref.abs().max() + 1e-30) + 1e-12
+            assert pt.allclose(g, ref, rtol=1e-3, atol=atol), (m, t, method)
 
 
 def test_export_accepts_two_dimensional_scalar_field(cuda, tmp_path):

@@ -133,6 +133,15 @@ def test_streamed_host_path_equals_resident_path(cuda, D, T, chunk):
     want = tables.interpolate(data.cuda(), pt.float32).cpu()
     got = tables.interpolate_host(data.pin_memory(), chunk_snapshots=chunk)
     assert not got.is_cuda and got.is_pinned() and pt.equal(got, want)
+    dma = tables.interpolate_host(data.pin_memory(), chunk_snapshots=chunk, gather=False)   # pitched DMA of all rows
+    assert pt.equal(dma, want)
+    zc = tables.interpolate_host(data.pin_memory(), chunk_snapshots=chunk, gather=True)     # PCIe gather of referenced rows
+    assert pt.equal(zc, want)
+    # a grid that references few source points takes the gather path by itself
+    few = KnnTables(KnnIndex(x.cuda()), q[:40].cuda(), 8)
+    assert few._compact()[0].numel() < 0.6 * x.size(0)
+    assert pt.equal(few.interpolate_host(data.pin_memory(), chunk_snapshots=chunk),
+                    few.interpolate(data.cuda(), pt.float32).cpu())
     again = tables.interpolate_host(data, out=got, chunk_snapshots=chunk)       # pageable input, buffers re-used
     assert again.data_ptr() == got.data_ptr() and pt.equal(again, want)
 
