@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--tune", default="", help="comma separated key=value pairs for s3_set_tuning, e.g. 5=1,8=0")
     ap.add_argument("--lattice-vertices", action="store_true", help="exact_topology=False")
+    ap.add_argument("--e2e", action="store_true", help="also time the host-to-host export (256 snapshots): DMA vs row gather")
     args = ap.parse_args()
     dev = pt.device("cuda", 0)
     pt.cuda.set_device(dev)
@@ -221,6 +222,24 @@ def main():
                     "gram_max_rel_err_vs_fp64": gram_err, "compute_svd_s_rank50_10_modes": t_svd,
                     "mode_orthonormality_err": ortho, "significant_modes": n_sig, "s_rel_err_top": float(((s_val.double() - lam).abs() / lam)[big].max())}
 
+    # ---- host-to-host export of a 256-snapshot batch: pitched DMA of all rows vs PCIe gather of the referenced rows
+    e2e_info = None
+    if args.e2e:
+        te = min(256, T)
+        host = out.new_empty((x.size(0), 1, te), device="cpu").pin_memory()
+        host.copy_(synth.wake_field(xd, 0, te, te, 1, wake["xc"], wake["yc"]))
+        res_h, e2e_info = None, {"snapshots": te, "referenced_fraction": int(pt.unique(tables.idx_sorted).numel()) / x.size(0)}
+        for label, g in (("dma", False), ("gather", True)):
+            res_h = tables.interpolate_host(host, out=res_h, gather=g)
+            pt.cuda.synchronize()
+            t0 = time.time()
+            for _ in range(3):
+                tables.interpolate_host(host, out=res_h, gather=g)
+            pt.cuda.synchronize()
+            e2e_info[f"{label}_ms"] = (time.time() - t0) / 3 * 1e3
+        want = tables.interpolate(host.to(dev), pt.float32).cpu()
+        assert pt.equal(res_h, want)
+
     n_unique = int(pt.unique(tables.idx_sorted).numel())
     b_algo = n_unique * T * 4 + nc * T * 4 + nc * k * 8
     peak = 6542.7
@@ -236,7 +255,7 @@ def main():
         "interp_ms": ms, "snapshot_points_per_s": nc * T / (ms * 1e-3), "unique_source_points": n_unique,
         "algorithmic_GBps": b_algo / (ms * 1e-3) / 1e9, "roofline_frac_of_measured": b_algo / (ms * 1e-3) / 1e9 / peak,
         "checks": "grid consistency, masks, knn idx/weights, interpolation tolerance, constant, linearity: ok",
-        "svd": svd_info,
+        "svd": svd_info, "e2e_256_snapshots": e2e_info,
     }))
 
 
