@@ -14,7 +14,7 @@ from .interpolate import interpolate_data, interp_gather
 from .knn import KnnIndex
 from .export import ExportData, Fields
 from .data import Datawriter, Dataloader, XDMFWriter
-from .svd import compute_svd
+from .svd import compute_svd, compute_svd_sharded
 from .utils import write_svd_s_cube_to_file
 from . import geometry
 
@@ -22,5 +22,5 @@ _logging.getLogger(__name__).addHandler(_logging.NullHandler())
 
 __version__ = "0.1.0"
 __all__ = ["SparseSpatialSampling", "SamplingTree", "list_geometries", "interpolate_data", "interp_gather", "KnnIndex",
-           "ExportData", "Fields", "Datawriter", "Dataloader", "XDMFWriter", "compute_svd", "write_svd_s_cube_to_file",
+           "ExportData", "Fields", "Datawriter", "Dataloader", "XDMFWriter", "compute_svd", "compute_svd_sharded", "write_svd_s_cube_to_file",
            "geometry"]

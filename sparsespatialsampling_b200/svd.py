@@ -111,27 +111,96 @@ def compute_svd(data_matrix: pt.Tensor, cell_area: pt.Tensor, rank: int = None, 
 
     mean = row_means(a)
     g = gram(a, mean, vol, vol_div, method)
+    s_out, u, v_out = _factor(a, mean, g, rank, n_modes, a.size(0))
+    if len(shape) == 3:
+        u = u.reshape(n_cells, vol_div, u.size(-1))
+    if home != dev:
+        pt.cuda.synchronize(dev)
+        return s_out.to(home), u.to(home), v_out.to(home)
+    return s_out, u, v_out
+
+
+def _factor(a: pt.Tensor, mean: pt.Tensor, g: pt.Tensor, rank, n_modes, rows_total: int):
+    """Eigen-decomposition of the (summed) Gram matrix and projection of the rows held in ``a``."""
+    t = a.size(1)
     lam, vec = pt.linalg.eigh(g)                       # ascending, fp64
     lam = pt.flip(lam, dims=(0,))
     vec = pt.flip(vec, dims=(1,))
     s_all = lam.clamp_min(0.0).sqrt()
-    r_max = min(a.size(0), t)
+    r_max = min(rows_total, t)
     if rank is None:
-        r = optimal_rank(s_all[:r_max], a.size(0), t)
+        r = optimal_rank(s_all[:r_max], rows_total, t)
     else:
         r = max(1, min(int(rank), r_max))
     s = s_all[:r]
     v = vec[:, :r]
     r_u = r if n_modes is None else max(1, min(int(n_modes), r))
-    live = s[:r_u] > 1e-6 * float(s_all[0]) if float(s_all[0]) > 0 else pt.zeros(r_u, dtype=pt.bool, device=dev)
+    live = s[:r_u] > 1e-6 * float(s_all[0]) if float(s_all[0]) > 0 else pt.zeros(r_u, dtype=pt.bool, device=a.device)
     inv_s = pt.where(live, 1.0 / s[:r_u].clamp_min(1e-300), pt.zeros_like(s[:r_u]))
     u = project(a, mean, v[:, :r_u] * inv_s.unsqueeze(0))
+    return s.to(pt.float32), u, v.to(pt.float32)
+
+
+def compute_svd_sharded(data_local: pt.Tensor, cell_area_local: pt.Tensor, rank: int = None, method: str = "tc3",
+                        n_modes: int = None, sharded_by: str = "cells", n_snapshots_total: int = None,
+                        gather_modes: bool = False, group=None) -> Tuple[pt.Tensor, pt.Tensor, pt.Tensor]:
+    """
+    ``compute_svd`` over several GPUs, one process per GPU ("SVD Gram").
+
+    The contraction runs over the cells, so the cells are sharded: every rank centres, weights and contracts its own
+    rows on the tensor cores, the ``T x T`` fp64 partial Gram matrices are summed with ONE all-reduce (32 MB at
+    T = 2000), every rank factors the identical sum and projects its own rows. Nothing else crosses the links.
+
+    :param data_local: ``sharded_by="cells"``: ``[n_local, T]`` / ``[n_local, D, T]``, the cells
+        ``parallel.row_window(N_cells, world, rank)``; ``sharded_by="time"``: ``[N_cells, (D,) T_s]``, the snapshot
+        window the sharded export left on this rank -- it is first transposed with ``parallel.time_to_row_shards``
+    :param cell_area_local: areas / volumes of the local cells (``"cells"``) or of all cells (``"time"``)
+    :param n_snapshots_total: T, required for ``sharded_by="time"``
+    :param gather_modes: all-gather U so that every rank returns all cells (default: the local rows only)
+    :return: ``(s [r], U [n_local | N_cells, (D,) r], V [T, r])`` on the device; ``s`` and ``V`` are identical on all ranks
+    """
+    from . import parallel
+    _lib.require_cuda()
+    if method not in GRAM_METHODS:
+        raise ValueError(f"unknown Gram method '{method}', available: {sorted(GRAM_METHODS)}")
+    if sharded_by not in ("cells", "time"):
+        raise ValueError(f"sharded_by must be 'cells' or 'time', got '{sharded_by}'")
+    if data_local.device.type != "cuda":
+        raise ValueError("compute_svd_sharded expects the shard in device memory (one process per GPU)")
+    dev = data_local.device
+    area = cell_area_local.detach().reshape(-1)
+    if sharded_by == "time":
+        if n_snapshots_total is None:
+            raise ValueError("sharded_by='time' needs n_snapshots_total")
+        n_cells_total = data_local.size(0)
+        if area.numel() != n_cells_total:
+            raise ValueError(f"cell_area has {area.numel()} entries for {n_cells_total} cells")
+        data_local = parallel.time_to_row_shards(data_local, n_snapshots_total, group)
+        if data_local.size(0) != n_cells_total:        # more than one rank: keep the areas of the local rows
+            import torch.distributed as dist
+            r0, r1 = parallel.row_window(n_cells_total, dist.get_world_size(group), dist.get_rank(group))
+            area = area[r0:r1]
+    shape = tuple(data_local.shape)
+    if len(shape) not in (2, 3):
+        raise ValueError(f"data_local must be [n, T] or [n, D, T], got {shape}")
+    if area.numel() != shape[0]:
+        raise ValueError(f"cell_area has {area.numel()} entries for {shape[0]} local cells")
+    n_local, t = shape[0], shape[-1]
+    vol_div = 1 if len(shape) == 2 else shape[1]
+    a = _as_device_matrix(data_local, dev).reshape(n_local * vol_div, t)
+    vol = area.to(device=dev, dtype=pt.float32).contiguous()
+
+    mean = row_means(a)
+    g = gram(a, mean, vol, vol_div, method)
+    counts = pt.tensor([a.size(0)], dtype=pt.int64, device=dev)
+    parallel.allreduce_sum(g, group)
+    parallel.allreduce_sum(counts, group)
+    rows_total = int(counts.item())
+    s_out, u, v_out = _factor(a, mean, g, rank, n_modes, rows_total)
     if len(shape) == 3:
-        u = u.reshape(n_cells, vol_div, r_u)
-    s_out, v_out = s.to(pt.float32), v.to(pt.float32)
-    if home != dev:
-        pt.cuda.synchronize(dev)
-        return s_out.to(home), u.to(home), v_out.to(home)
+        u = u.reshape(n_local, vol_div, u.size(-1))
+    if gather_modes:
+        u = parallel.gather_rows(u, rows_total // vol_div, group)
     return s_out, u, v_out
 
 

@@ -52,3 +52,43 @@ def test_snapshot_sharded_interpolation_world_size_2(tmp_path):
     full = np.load(tmp_path / "full.npy")
     assert np.array_equal(np.concatenate(parts, axis=2), full)
     assert np.array_equal(np.load(tmp_path / "centers0.npy"), np.load(tmp_path / "centers1.npy"))
+
+
+def _svd_exchange_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparsespatialsampling_b200.parallel import (snapshot_window, row_window, time_to_row_shards, allreduce_sum,
+                                                     gather_rows)
+    rng = np.random.default_rng(1)                     # same data on every rank
+    Nc, D, T = 37, 2, 13                               # odd sizes: unequal windows on both axes
+    full = rng.standard_normal((Nc, D, T)).astype(np.float32)
+    vol = rng.random(Nc) + 0.5
+    t0, t1 = snapshot_window(T, world, rank)
+    rows = time_to_row_shards(pt.from_numpy(full[:, :, t0:t1].copy()), T)
+    r0, r1 = row_window(Nc, world, rank)
+    assert np.array_equal(rows.numpy(), full[r0:r1])
+    rows2d = time_to_row_shards(pt.from_numpy(full[:, 0, t0:t1].copy()), T)
+    assert np.array_equal(rows2d.numpy(), full[r0:r1, 0])
+    # local weighted Gram of the own rows (oracle arithmetic), summed over the ranks == Gram of the whole matrix
+    g = pt.from_numpy(orc.weighted_gram(rows.numpy().reshape(-1, T), np.repeat(vol[r0:r1], D)))
+    allreduce_sum(g)
+    everything = gather_rows(rows, Nc)
+    assert np.array_equal(everything.numpy(), full)
+    np.save(os.path.join(tmp, f"gram{rank}.npy"), g.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_svd_exchange_world_size_3(tmp_path):
+    """time -> cell re-sharding, all-reduce of the partial Gram matrices and the row gather of compute_svd_sharded."""
+    world = 3
+    mp.spawn(_svd_exchange_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(1)
+    full = rng.standard_normal((37, 2, 13)).astype(np.float32)
+    vol = rng.random(37) + 0.5
+    ref = orc.weighted_gram(full.reshape(-1, 13), np.repeat(vol, 2))
+    for r in range(world):
+        g = np.load(tmp_path / f"gram{r}.npy")
+        assert np.allclose(g, ref, rtol=1e-12, atol=1e-12)
+        assert np.array_equal(g, np.load(tmp_path / "gram0.npy"))
