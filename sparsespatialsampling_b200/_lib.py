@@ -96,6 +96,10 @@ def load():
             fn.restype = res
             fn.argtypes = args
         _lib = lib
+        # S3B200_TUNE="key=value,...": kernel tuning knobs (s3_set_tuning) applied at load, for A/B runs of the tests
+        for kv in [t for t in os.environ.get("S3B200_TUNE", "").split(",") if t]:
+            key, value = kv.split("=")
+            check(lib.s3_set_tuning(int(key), int(value)))
     return _lib
 
 

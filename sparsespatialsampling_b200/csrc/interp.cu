@@ -28,6 +28,7 @@ static int g_cells_per_cta = 4;
 static int g_direct_variant = 1;   // 0 = CTA walks cells, 1 = warp per cell (s3_set_tuning key 3)
 static int g_warps_per_cta = 8;
 static int g_direct_regs = 0;      // k = 8 / 26: (idx, w) in registers instead of shuffle broadcasts (s3_set_tuning key 8)
+static int g_bcast = 0;            // (idx, w) broadcast in the warp-per-cell kernels: 0 = SHFL, 1 = REDUX.OR (s3_set_tuning key 13)
 static int g_direct_window = 1;    // k > 16: window formulation of the warp-per-cell kernel (s3_set_tuning key 12)
 static int g_chunk_cols = 0;       // columns per grid.y window of the warp-per-cell kernel, 0 = by k (s3_set_tuning key 9)
 static int g_direct_sync = 0;      // barrier per column step in the warp-per-cell kernel (s3_set_tuning key 7)
@@ -123,6 +124,25 @@ interp_gather_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_
     }
 }
 
+// Broadcast of lane `src`'s value to the whole warp. BCAST = 0: SHFL (one wavefront of the LSU / L1 data pipe -- the
+// pipe that bounds the warp-per-cell kernel). BCAST = 1: REDUX.OR over (lane == src ? bits : 0): no L1 wavefront, the
+// result lands in a uniform register.
+template <int BCAST>
+__device__ __forceinline__ uint32_t bcast_bits(uint32_t v, int src, int lane) {
+    if (BCAST == 1) return __reduce_or_sync(0xffffffffu, lane == src ? v : 0u);
+    return __shfl_sync(0xffffffffu, v, src);
+}
+template <int BCAST>
+__device__ __forceinline__ int32_t bcast(int32_t v, int src, int lane) { return (int32_t)bcast_bits<BCAST>((uint32_t)v, src, lane); }
+template <int BCAST>
+__device__ __forceinline__ float bcast(float v, int src, int lane) { return __uint_as_float(bcast_bits<BCAST>(__float_as_uint(v), src, lane)); }
+template <int BCAST>
+__device__ __forceinline__ double bcast(double v, int src, int lane) {
+    const uint32_t lo = bcast_bits<BCAST>((uint32_t)__double2loint(v), src, lane);
+    const uint32_t hi = bcast_bits<BCAST>((uint32_t)__double2hiint(v), src, lane);
+    return __hiloint2double((int)hi, (int)lo);
+}
+
 // Warp-per-cell variant: the warps of a CTA work on CONSECUTIVE cells (Morton neighbours) and sweep the row in
 // lock step, 128 columns (one 128-bit vector per lane) at a time. Neighbouring cells share most of their source
 // rows, so the same 512-byte row segments are requested by several warps of the CTA within a few hundred cycles
@@ -136,7 +156,7 @@ interp_gather_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_
 // inside the L2 for long rows. The un-chunked instantiation is kept byte for byte: this kernel's speed depends on
 // the load/FMA interleaving ptxas picks for the neighbour loop (an explicit 4-deep batching measured 25 % slower, a
 // different loop bound 10 % slower).
-template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL, bool SYNC, bool CHUNKED>
+template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL, bool SYNC, bool CHUNKED, int BCAST = 0>
 __global__ void __launch_bounds__(512)
 interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
                        const Tw* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
@@ -174,8 +194,10 @@ interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int3
         // at ~2 cycles each), not by latency; batching 8 neighbours' loads per lane (tried) only lowered the L1 hit
         // rate and cost 25 %.  The UNROLL column vectors of one neighbour are independent loads.
         for (int j = 0; j < k; ++j) {
-            const int32_t r = __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
-            const Tw wj = __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            const int32_t r = BCAST ? bcast<BCAST>((j & 32) ? idx_hi : idx_lo, j & 31, lane)
+                                    : __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
+            const Tw wj = BCAST ? bcast<BCAST>((j & 32) ? w_hi : w_lo, j & 31, lane)
+                                : __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
             const Tin* src = data + (int64_t)r * (CHUNKED ? row_stride : row_len) + col0 + lane * V;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -206,7 +228,7 @@ interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int3
 // blockIdx.y is swept with absolute column indices. Functionally identical to the CHUNKED instantiation above; it exists
 // because ptxas schedules its neighbour loop differently (more loads in flight per warp), which measured 8-10 % faster
 // for k = 26 with two column vectors per lane (C4: 7.0 ms vs 7.8 ms) and 10 % slower for k = 8 with one.
-template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL>
+template <typename Tin, typename Tw, typename Tout, int V, int MODE, int UNROLL, int BCAST = 0>
 __global__ void __launch_bounds__(512)
 interp_warpcell_window_kernel(const Tin* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
                               const Tw* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
@@ -231,8 +253,10 @@ interp_warpcell_window_kernel(const Tin* __restrict__ data, int64_t row_len, con
 #pragma unroll
             for (int e = 0; e < V; ++e) acc[u][e] = (Tw)0;
         for (int j = 0; j < k; ++j) {
-            const int32_t r = __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
-            const Tw wj = __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            const int32_t r = BCAST ? bcast<BCAST>((j & 32) ? idx_hi : idx_lo, j & 31, lane)
+                                    : __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
+            const Tw wj = BCAST ? bcast<BCAST>((j & 32) ? w_hi : w_lo, j & 31, lane)
+                                : __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
             const Tin* src = data + (int64_t)r * row_len + col0 + lane * V;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -371,8 +395,19 @@ static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, 
         reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk)
         const bool sync = g_direct_sync != 0;
         if (k > 16 && vec_ok && unroll == 2 && !sync && g_direct_window != 0) {
+            if (g_bcast == 1)
+                interp_warpcell_window_kernel<Tin, Tw, Tout, VFULL, MODE, 2, 1><<<wc_grid, warps * 32, 0, stream>>>(
+                    reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, chunk);
+            else
             interp_warpcell_window_kernel<Tin, Tw, Tout, VFULL, MODE, 2><<<wc_grid, warps * 32, 0, stream>>>(
                 reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, chunk);
+        } else if (g_bcast == 1 && n_chunks == 1 && vec_ok && !sync) {
+            if (unroll == 2)
+                interp_warpcell_kernel<Tin, Tw, Tout, VFULL, MODE, 2, false, false, 1><<<wc_grid, warps * 32, 0, stream>>>(
+                    reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk);
+            else
+                interp_warpcell_kernel<Tin, Tw, Tout, VFULL, MODE, 1, false, false, 1><<<wc_grid, warps * 32, 0, stream>>>(
+                    reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk);
         } else if (n_chunks > 1 && vec_ok) {
             if (unroll == 2) S3_WARPCELL(VFULL, 2, false, true); else S3_WARPCELL(VFULL, 1, false, true);
         } else if (vec_ok && unroll == 2) {
@@ -457,6 +492,11 @@ extern "C" int s3_set_tuning(int key, int value) {
     if (key == 9) {
         S3_REQUIRE(value >= 0, "s3_set_tuning: window columns must be >= 0");
         s3::g_chunk_cols = value;
+        return S3_OK;
+    }
+    if (key == 13) {
+        S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: broadcast must be 0 (SHFL) or 1 (REDUX)");
+        s3::g_bcast = value;
         return S3_OK;
     }
     if (key == 12) {
