@@ -196,6 +196,9 @@ def run_ours(args):
     os.dup2(2, 1)
     pt.cuda.set_device(local)
     dev = pt.device("cuda", local)
+    # host cores + pinned buffers on the NUMA node of this rank's GPU (the e2e leg moves 1.9 GB/step over PCIe)
+    from sparsespatialsampling_b200.parallel import bind_to_gpu_numa_node
+    numa_cores = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -412,6 +415,7 @@ def run_ours(args):
                    "fields": "p[D=1] + U[D=2]", "snapshots_per_gpu": N_SNAP, "unique_source_points": n_unique,
                    "l2_policy": "inputs larger than L2 (1.2 GB of snapshot rows per step vs 126 MB L2)",
                    "sharding": "snapshot window per rank; grid + KNN tables broadcast once over NCCL",
+                   "host_cores_bound_to_gpu_numa_node": len(numa_cores) if numa_cores else None,
                    "kernel": args.kernel, "chunk_cols": args.chunk_cols,
                    "unique_rows_per_tile_sum": tables.tiles.total_rows if args.kernel != "direct" else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -457,6 +461,7 @@ def main():
     ap.add_argument("--variant", type=int, default=-1, help="direct kernel: 0 = CTA walks cells, 1 = warp per cell")
     ap.add_argument("--warps", type=int, default=0, help="warp-per-cell kernel: warps (= cells) per CTA")
     ap.add_argument("--unroll", type=int, default=0, help="warp-per-cell kernel: column vectors per lane and step")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--tune", default="", help="comma separated key=value pairs for s3_set_tuning, e.g. 5=1,9=512")
     ap.add_argument("--regs", type=int, default=-1, help="warp-per-cell kernel: 1 = (idx, w) in registers (k = 8 | 26)")
     ap.add_argument("--sync", type=int, default=-1, help="warp-per-cell kernel: 1 = barrier per column step")

@@ -11,10 +11,54 @@ over the cells, so the time-sharded result of the export is first turned into ro
 (``time_to_row_shards``, one point-to-point block per rank pair), every rank contracts its own rows and the ``T x T``
 partial Gram matrices are summed with one all-reduce (``allreduce_sum``), see ``svd.compute_svd_sharded``.
 """
-from typing import List, Tuple
+import logging
+import os
+from typing import List, Optional, Tuple
 
 import torch as pt
 import torch.distributed as dist
+
+logger = logging.getLogger(__name__)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """
+    Pin the calling process to the host cores NVML reports as local to GPU ``device_index`` (its NUMA node).
+
+    The streamed export moves every snapshot batch through pinned host memory at PCIe rate; pinned pages are placed on
+    the NUMA node of the allocating thread, so a rank that runs on the other socket pays an inter-socket hop per byte
+    in both directions (and, with several ranks, all of them queue on one memory controller). Call this once per
+    process BEFORE allocating host buffers -- what ``numactl --cpunodebind`` does for a hand-launched job.
+    Returns the core list, or ``None`` when NVML or the affinity call is unavailable (nothing is changed then).
+    """
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = device_index
+            if visible:
+                entry = visible.split(",")[device_index].strip()
+                if entry.isdigit():
+                    index = int(entry)
+                    handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+                else:
+                    handle = pynvml.nvmlDeviceGetHandleByUUID(entry)
+            else:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            n_cpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = local & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except Exception as e:                              # no NVML / not permitted: keep the scheduler's placement
+        logger.debug("bind_to_gpu_numa_node: %s", e)
+        return None
 
 
 def snapshot_window(n_snapshots: int, world_size: int, rank: int) -> Tuple[int, int]:
