@@ -111,6 +111,25 @@ def case_definitions(geo):
                          g.SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"], refine=True,
                                           min_refinement_level=8)],
         kwargs=dict(uniform_level=3, min_metric=0.5, n_cells_iter_start=10, max_delta_level=True))
+    # the second stopping rule (s_cube.py:263-284: metric within reach_at_least of the target and improving by less than
+    # relTol), a cells-per-iteration schedule that decays (n_cells_iter_end < start, s_cube.py:286-315) and a box used as a
+    # body (keep_inside=False). pre_select=True cannot be pinned with analytic shapes: no cell is ever removed then, every
+    # node id stays in use and the reference fails in renumber_node_indices_parallel (numba cannot type the empty set).
+    x = synth.cylinder2d_cloud(5000, seed=21)
+    cases["g2d_reltol"] = dict(
+        coords=x, metric=synth.wake_metric(x),
+        geoms=lambda g: [g.CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"]),
+                         g.SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"]),
+                         g.CubeGeometry("block", False, [1.2, 0.05], [1.5, 0.15])],
+        kwargs=dict(uniform_level=3, min_metric=0.9, n_cells_iter_start=40, n_cells_iter_end=4, relTol=4e-3,
+                    reach_at_least=0.5))
+    # 3-D: delta-level constraint together with geometry refinement of a sphere and of the domain box, stop by n_cells
+    x = synth.cylinder3d_cloud(5000, seed=22)
+    cases["g3d_delta_geo"] = dict(
+        coords=x, metric=synth.wake_metric(x, xc=0.8, yc=1.0),
+        geoms=lambda g: [g.CubeGeometry("domain", True, synth.CYL3D["lower"], synth.CYL3D["upper"]),
+                         g.SphereGeometry("ball", False, [0.8, 1.0, 0.15], 0.12, refine=True, min_refinement_level=5)],
+        kwargs=dict(uniform_level=2, n_cells=700, n_cells_iter_start=12, max_delta_level=True))
     return cases
 
 

@@ -28,7 +28,8 @@ def _run(case, **extra):
     return tree
 
 
-@pytest.mark.parametrize("name", ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta", "g3d_delta", "g2d_delta_geo"])
+@pytest.mark.parametrize("name", ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta", "g3d_delta", "g2d_delta_geo",
+                                  "g2d_reltol", "g3d_delta_geo"])
 def test_refine_matches_reference_golden(cuda, name):
     import sparsespatialsampling_b200.geometry as geo
     case = case_definitions(geo)[name]

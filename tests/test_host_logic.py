@@ -11,7 +11,7 @@ from tests.golden.make_golden import case_definitions
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta"])
+@pytest.mark.parametrize("name", ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta", "g2d_reltol"])
 def test_oracle_reproduces_reference_golden(name):
     # pins the oracle to outputs of the reference itself (leaf cells, numbering, gains, metrics: bit-exact)
     import sparsespatialsampling_b200.geometry as geo

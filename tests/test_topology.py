@@ -16,7 +16,8 @@ from oracle.topology_oracle import OracleTopology, neighbour_table, slot_directi
 from tests.golden.make_golden import case_definitions
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta", "g3d_delta", "g2d_delta_geo"]
+CASES = ["g2d_metric", "g2d_ncells", "g3d_metric", "g2d_delta", "g3d_delta", "g2d_delta_geo", "g2d_reltol",
+         "g3d_delta_geo"]
 
 
 def _product_topology(d, center, width):
