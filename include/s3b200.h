@@ -38,8 +38,9 @@ int64_t s3_launch_count(void);
 
 /* tuning knobs (benchmarking): key 0 = cells per CTA of the direct interpolation kernel, ...,
  * key 10 = 16-row K-blocks accumulated in TMEM per segment of the tensor-core Gram kernel (default 8),
- * key 11 = segments summed in fp32 registers per fp64 flush (default 128), key 14 = Gram kernel in clusters of two
- * CTAs that share the B operand by TMA multicast (default 1) */
+ * key 11 = segments summed in fp32 registers per fp64 flush (default 128), key 13 = how a warp of the interpolation
+ * kernel broadcasts a cell's (index, weight) pairs: -1 by k (default), 0 SHFL, 1 REDUX, 2 / 3 shared memory,
+ * key 14 = Gram kernel in clusters of two CTAs that share the B operand by TMA multicast (default 1) */
 int s3_set_tuning(int key, int value);
 
 /* ---- k-nearest-neighbour index over the original point cloud ---------------------------------

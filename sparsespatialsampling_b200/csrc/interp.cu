@@ -28,7 +28,8 @@ static int g_cells_per_cta = 4;
 static int g_direct_variant = 1;   // 0 = CTA walks cells, 1 = warp per cell (s3_set_tuning key 3)
 static int g_warps_per_cta = 8;
 static int g_direct_regs = 0;      // k = 8 / 26: (idx, w) in registers instead of shuffle broadcasts (s3_set_tuning key 8)
-static int g_bcast = 0;            // (idx, w) broadcast in the warp-per-cell kernels: 0 = SHFL, 1 = REDUX.OR (s3_set_tuning key 13)
+static int g_bcast = -1;           // (idx, w) broadcast in the warp-per-cell kernels: 0 = SHFL, 1 = REDUX.OR, 2 / 3 = LDS.64 / LDS.128 from
+                                   // shared memory, -1 = by k (k > 16: 2, else 0; measured) (s3_set_tuning key 13)
 static int g_direct_window = 1;    // k > 16: window formulation of the warp-per-cell kernel (s3_set_tuning key 12)
 static int g_chunk_cols = 0;       // columns per grid.y window of the warp-per-cell kernel, 0 = by k (s3_set_tuning key 9)
 static int g_direct_sync = 0;      // barrier per column step in the warp-per-cell kernel (s3_set_tuning key 7)
@@ -180,6 +181,17 @@ interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int3
     const int64_t orow = !active ? 0 : (out_row ? (int64_t)out_row[cell] : cell);
     Tout* o = out + orow * (CHUNKED ? row_stride : row_len);
     constexpr int STEP = 32 * V;
+    // BCAST >= 2: the warp parks its (index, weight) pairs in shared memory; the neighbour loop reads them back with one
+    // uniform LDS.64 (BCAST 2) or one LDS.128 per two neighbours (BCAST 3) instead of two SHFL per neighbour.
+    extern __shared__ int2 s_pairs[];
+    const int pair_stride = (k + 1) & ~1;
+    int2* my_pairs = s_pairs + warp * pair_stride;
+    if (BCAST >= 2) {
+        if (lane < k) my_pairs[lane] = make_int2(idx_lo, __float_as_int((float)w_lo));
+        if (lane + 32 < k) my_pairs[lane + 32] = make_int2(idx_hi, __float_as_int((float)w_hi));
+        if (lane == 0 && (k & 1)) my_pairs[k] = make_int2(0, 0);
+        __syncwarp();
+    }
     for (int64_t col0 = 0; col0 < row_len; col0 += (int64_t)STEP * UNROLL) {
         if (SYNC) {
             __syncthreads();
@@ -193,11 +205,46 @@ interp_warpcell_kernel(const Tin* __restrict__ data, int64_t row_len, const int3
         // One neighbour at a time on purpose: ncu shows this kernel bound by the L1 data pipe (LDG.128 = 4 wavefronts
         // at ~2 cycles each), not by latency; batching 8 neighbours' loads per lane (tried) only lowered the L1 hit
         // rate and cost 25 %.  The UNROLL column vectors of one neighbour are independent loads.
+        if (BCAST == 3) {
+            // two neighbours per LDS.128; a zero-weight pad entry (row 0) completes an odd k
+            const int4* my_quads = reinterpret_cast<const int4*>(my_pairs);
+            for (int j = 0; j < k; j += 2) {
+                const int4 q = my_quads[j >> 1];
+                const Tin* src0 = data + (int64_t)q.x * (CHUNKED ? row_stride : row_len) + col0 + lane * V;
+                const Tin* src1 = data + (int64_t)q.z * (CHUNKED ? row_stride : row_len) + col0 + lane * V;
+                const Tw w0 = (Tw)__int_as_float(q.y), w1 = (Tw)__int_as_float(q.w);
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (col0 + u * STEP + lane * V < row_len) {
+                        const Vec<Tin, V> x0 = ld_stream<Tin, V>(src0 + u * STEP);
+                        const Vec<Tin, V> x1 = ld_stream<Tin, V>(src1 + u * STEP);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            if (MODE == 0) {
+                                acc[u][e] = fmaf((float)w0, (float)x0.v[e], (float)acc[u][e]);
+                                if (j + 1 < k) acc[u][e] = fmaf((float)w1, (float)x1.v[e], (float)acc[u][e]);
+                            } else {
+                                acc[u][e] = __dadd_rn((double)acc[u][e], __dmul_rn((double)w0, (double)x0.v[e]));
+                                if (j + 1 < k) acc[u][e] = __dadd_rn((double)acc[u][e], __dmul_rn((double)w1, (double)x1.v[e]));
+                            }
+                        }
+                    }
+                }
+            }
+        } else
         for (int j = 0; j < k; ++j) {
-            const int32_t r = BCAST ? bcast<BCAST>((j & 32) ? idx_hi : idx_lo, j & 31, lane)
-                                    : __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
-            const Tw wj = BCAST ? bcast<BCAST>((j & 32) ? w_hi : w_lo, j & 31, lane)
-                                : __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            int32_t r;
+            Tw wj;
+            if (BCAST == 2) {
+                const int2 pr = my_pairs[j];
+                r = pr.x;
+                wj = (Tw)__int_as_float(pr.y);
+            } else {
+                r = BCAST ? bcast<BCAST>((j & 32) ? idx_hi : idx_lo, j & 31, lane)
+                          : __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
+                wj = BCAST ? bcast<BCAST>((j & 32) ? w_hi : w_lo, j & 31, lane)
+                           : __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            }
             const Tin* src = data + (int64_t)r * (CHUNKED ? row_stride : row_len) + col0 + lane * V;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -246,17 +293,60 @@ interp_warpcell_window_kernel(const Tin* __restrict__ data, int64_t row_len, con
     const int64_t orow = out_row ? (int64_t)out_row[cell] : cell;
     Tout* o = out + orow * row_len;
     constexpr int STEP = 32 * V;
+    extern __shared__ int2 s_pairs[];                      // BCAST >= 2, see interp_warpcell_kernel
+    const int pair_stride = (k + 1) & ~1;
+    int2* my_pairs = s_pairs + warp * pair_stride;
+    if (BCAST >= 2) {
+        if (lane < k) my_pairs[lane] = make_int2(idx_lo, __float_as_int((float)w_lo));
+        if (lane + 32 < k) my_pairs[lane + 32] = make_int2(idx_hi, __float_as_int((float)w_hi));
+        if (lane == 0 && (k & 1)) my_pairs[k] = make_int2(0, 0);
+        __syncwarp();
+    }
     for (int64_t col0 = col_begin; col0 < col_end; col0 += (int64_t)STEP * UNROLL) {
         Tw acc[UNROLL][V];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
             for (int e = 0; e < V; ++e) acc[u][e] = (Tw)0;
+        if (BCAST == 3) {
+            const int4* my_quads = reinterpret_cast<const int4*>(my_pairs);
+            for (int j = 0; j < k; j += 2) {
+                const int4 q = my_quads[j >> 1];
+                const Tin* src0 = data + (int64_t)q.x * row_len + col0 + lane * V;
+                const Tin* src1 = data + (int64_t)q.z * row_len + col0 + lane * V;
+                const Tw w0 = (Tw)__int_as_float(q.y), w1 = (Tw)__int_as_float(q.w);
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (col0 + u * STEP + lane * V < col_end) {
+                        const Vec<Tin, V> x0 = ld_stream<Tin, V>(src0 + u * STEP);
+                        const Vec<Tin, V> x1 = ld_stream<Tin, V>(src1 + u * STEP);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            if (MODE == 0) {
+                                acc[u][e] = fmaf((float)w0, (float)x0.v[e], (float)acc[u][e]);
+                                if (j + 1 < k) acc[u][e] = fmaf((float)w1, (float)x1.v[e], (float)acc[u][e]);
+                            } else {
+                                acc[u][e] = __dadd_rn((double)acc[u][e], __dmul_rn((double)w0, (double)x0.v[e]));
+                                if (j + 1 < k) acc[u][e] = __dadd_rn((double)acc[u][e], __dmul_rn((double)w1, (double)x1.v[e]));
+                            }
+                        }
+                    }
+                }
+            }
+        } else
         for (int j = 0; j < k; ++j) {
-            const int32_t r = BCAST ? bcast<BCAST>((j & 32) ? idx_hi : idx_lo, j & 31, lane)
-                                    : __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
-            const Tw wj = BCAST ? bcast<BCAST>((j & 32) ? w_hi : w_lo, j & 31, lane)
-                                : __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            int32_t r;
+            Tw wj;
+            if (BCAST == 2) {
+                const int2 pr = my_pairs[j];
+                r = pr.x;
+                wj = (Tw)__int_as_float(pr.y);
+            } else {
+                r = BCAST ? bcast<BCAST>((j & 32) ? idx_hi : idx_lo, j & 31, lane)
+                          : __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
+                wj = BCAST ? bcast<BCAST>((j & 32) ? w_hi : w_lo, j & 31, lane)
+                           : __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            }
             const Tin* src = data + (int64_t)r * row_len + col0 + lane * V;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -394,13 +484,29 @@ static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, 
     interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, SS, CC><<<wc_grid, warps * 32, 0, stream>>>(               \
         reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk)
         const bool sync = g_direct_sync != 0;
+        const int g_bcast = s3::g_bcast >= 0 ? s3::g_bcast : (k > 16 ? 2 : 0);      // shadows the knob: resolved per call
         if (k > 16 && vec_ok && unroll == 2 && !sync && g_direct_window != 0) {
-            if (g_bcast == 1)
+            const size_t pairs_smem = (size_t)warps * ((k + 1) & ~1) * sizeof(int2);
+            if (g_bcast == 2 && std::is_same<Tw, float>::value)
+                interp_warpcell_window_kernel<Tin, Tw, Tout, VFULL, MODE, 2, 2><<<wc_grid, warps * 32, pairs_smem, stream>>>(
+                    reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, chunk);
+            else if (g_bcast == 3 && std::is_same<Tw, float>::value)
+                interp_warpcell_window_kernel<Tin, Tw, Tout, VFULL, MODE, 2, 3><<<wc_grid, warps * 32, pairs_smem, stream>>>(
+                    reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, chunk);
+            else if (g_bcast == 1)
                 interp_warpcell_window_kernel<Tin, Tw, Tout, VFULL, MODE, 2, 1><<<wc_grid, warps * 32, 0, stream>>>(
                     reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, chunk);
             else
             interp_warpcell_window_kernel<Tin, Tw, Tout, VFULL, MODE, 2><<<wc_grid, warps * 32, 0, stream>>>(
                 reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, chunk);
+        } else if (g_bcast >= 2 && n_chunks == 1 && vec_ok && !sync && std::is_same<Tw, float>::value) {
+            const size_t pairs_smem = (size_t)warps * ((k + 1) & ~1) * sizeof(int2);
+#define S3_WARPCELL_LDS(UU, BB)                                                                                  \
+    interp_warpcell_kernel<Tin, Tw, Tout, VFULL, MODE, UU, false, false, BB><<<wc_grid, warps * 32, pairs_smem, stream>>>( \
+        reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk)
+            if (g_bcast == 2) { if (unroll == 2) S3_WARPCELL_LDS(2, 2); else S3_WARPCELL_LDS(1, 2); }
+            else { if (unroll == 2) S3_WARPCELL_LDS(2, 3); else S3_WARPCELL_LDS(1, 3); }
+#undef S3_WARPCELL_LDS
         } else if (g_bcast == 1 && n_chunks == 1 && vec_ok && !sync) {
             if (unroll == 2)
                 interp_warpcell_kernel<Tin, Tw, Tout, VFULL, MODE, 2, false, false, 1><<<wc_grid, warps * 32, 0, stream>>>(
@@ -495,7 +601,7 @@ extern "C" int s3_set_tuning(int key, int value) {
         return S3_OK;
     }
     if (key == 13) {
-        S3_REQUIRE(value == 0 || value == 1, "s3_set_tuning: broadcast must be 0 (SHFL) or 1 (REDUX)");
+        S3_REQUIRE(value >= -1 && value <= 3, "s3_set_tuning: broadcast must be -1 (by k), 0 (SHFL), 1 (REDUX), 2 (LDS.64) or 3 (LDS.128)");
         s3::g_bcast = value;
         return S3_OK;
     }
