@@ -417,10 +417,11 @@ def run_ours(args):
                    "sharding": "snapshot window per rank; grid + KNN tables broadcast once over NCCL",
                    "host_cores_bound_to_gpu_numa_node": len(numa_cores) if numa_cores else None,
                    "kernel": args.kernel, "chunk_cols": args.chunk_cols,
-                   "unique_rows_per_tile_sum": tables.tiles.total_rows if args.kernel != "direct" else None},
+                   "unique_rows_per_tile_sum": tables.tiles.total_rows if args.kernel in ("staged", "pipe") else None,
+                   "rows_loaded_per_cell": tables.groups.rows_per_cell if args.kernel == "grouped" else float(k)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": {"staged": "interp_staged_kernel", "pipe": "interp_pipe_kernel",
-                                "direct": "interp_warpcell_kernel"}[args.kernel],
+                                "direct": "interp_warpcell_kernel", "grouped": "interp_group_kernel"}[args.kernel],
                      "algorithmic_bytes_per_step": b_algo, "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -454,7 +455,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="s3b200", choices=["s3b200", "reference"])
-    ap.add_argument("--kernel", default="direct", choices=["staged", "direct", "pipe"], help="interpolation kernel variant")
+    ap.add_argument("--kernel", default="direct", choices=["staged", "direct", "pipe", "grouped"], help="interpolation kernel variant")
     ap.add_argument("--cells-per-cta", type=int, default=0, help="direct kernel: cells per CTA (0 = library default)")
     ap.add_argument("--staging", type=int, default=-1, help="staged kernel: 0 = TMA bulk copies, 1 = cp.async")
     ap.add_argument("--stage-kb", type=int, default=0, help="staged kernel: shared-memory budget per CTA in KB")

@@ -40,6 +40,8 @@ int64_t s3_launch_count(void);
  * key 10 = 16-row K-blocks accumulated in TMEM per segment of the tensor-core Gram kernel (default 8),
  * key 11 = segments summed in fp32 registers per fp64 flush (default 128), key 13 = how a warp of the interpolation
  * kernel broadcasts a cell's (index, weight) pairs: -1 by k (default), 0 SHFL, 1 REDUX, 2 / 3 shared memory,
+ * 4 byte-offset table; keys 15-18 = grouped kernel: warps per CTA, distinct rows in flight per lane (1, 2, 3, 4, 6,
+ * 8), CTAs per SM the register allocation must allow (2..6), column vectors per lane (1, 2),
  * key 14 = Gram kernel in clusters of two CTAs that share the B operand by TMA multicast (default 1) */
 int s3_set_tuning(int key, int value);
 
@@ -172,6 +174,23 @@ int s3_sumsq(const double* d_x, int64_t n, double* d_out, void* stream);
 int s3_interp_gather(const void* d_data, int data_dtype, int64_t n_src, int64_t row_len,
                      const int32_t* d_idx, const void* d_w, int64_t n_cells, int k,
                      const int32_t* d_out_row, void* d_out, int out_dtype, void* stream);
+
+/* Grouped fp32 variant of the same operator (experimental): a warp interpolates
+ * s3_interp_group_size() = 4 consecutive cells (processing order) and loads every DISTINCT source row of
+ * the group once, folding it into up to 4 accumulators.
+ * s3_interp_groups_build (once per KNN cache): from d_idx int32 / d_w fp32 [n_cells, k] builds, per group g
+ *   (n_groups = ceil(n_cells / 4)): d_cnt int32 [n_groups] number of distinct rows, d_ent int32
+ *   [n_groups, 4*k, 2] = {row, membership mask} in order of first appearance, d_wts fp32 [n_groups, 4*k, 4]
+ *   weight of the row for each cell of the group (0 = not referenced).
+ * s3_interp_grouped: same result as s3_interp_gather(F32, F32) up to the fp32 summation order (terms of a
+ *   cell are added in the order of the group's list). Requires row_len % 4 == 0 and 16-byte aligned
+ *   buffers. A row a cell does not reference is skipped by predicate, never multiplied by zero.       */
+int s3_interp_group_size(void);
+int s3_interp_groups_build(const int32_t* d_idx, const float* d_w, int64_t n_cells, int k, int32_t* d_cnt,
+                           void* d_ent, void* d_wts, void* stream);
+int s3_interp_grouped(const void* d_data, int64_t n_src, int64_t row_len, const int32_t* d_cnt,
+                      const void* d_ent, const void* d_wts, int64_t n_cells, int k,
+                      const int32_t* d_out_row, void* d_out, int out_dtype, void* stream);
 
 /* Staged fp32 variant of the same operator: cells are grouped in tiles of 32 (processing order); the
  * unique source rows of a tile are copied once into shared memory by TMA bulk copies and re-used by

@@ -65,6 +65,10 @@ _SIGNATURES = {
     "s3_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "s3_interp_gather": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                  c_void_p, c_int, c_void_p]),
+    "s3_interp_group_size": (c_int, []),
+    "s3_interp_groups_build": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "s3_interp_grouped": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                  c_void_p, c_int, c_void_p]),
     "s3_interp_tiles_build": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "s3_interp_staged": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),

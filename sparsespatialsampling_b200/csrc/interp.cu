@@ -22,6 +22,7 @@ extern int g_pipe_prefetch;
 extern int g_tc_seg_kblocks;
 extern int g_tc_flush_segments;
 extern int g_tc_pair;
+int set_group_tuning(int key, int value);
 constexpr int kInterpThreads = 128;
 constexpr int kMaxCellsPerCta = 32;
 static int g_cells_per_cta = 4;
@@ -373,6 +374,68 @@ interp_warpcell_window_kernel(const Tin* __restrict__ data, int64_t row_len, con
     }
 }
 
+// Offset-table variant (fp32 in, fp32 weights): per neighbour the generic kernels spend ~24 instructions, most of them
+// on the broadcast and on the 64-bit address r * row_len * 4 + base. Here the warp computes the BYTE OFFSET of each of
+// its k source rows once per cell, parks {offset lo, offset hi, weight} in shared memory (16 B per neighbour) and the
+// neighbour loop is LDS.128 (uniform address, one wavefront) -> 64-bit add -> LDG.128 -> 4 FFMA. Column windows as in
+// interp_warpcell_window_kernel (blockIdx.y).
+template <typename Tout, int V, int UNROLL>
+__global__ void __launch_bounds__(512)
+interp_warpcell_off_kernel(const float* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
+                           const float* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
+                           Tout* __restrict__ out, int64_t chunk_cols) {
+    extern __shared__ int4 s_quads[];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t cell = (int64_t)blockIdx.x * warps + warp;
+    if (cell >= n_cells) return;
+    const int64_t col_begin = (int64_t)blockIdx.y * chunk_cols;
+    const int64_t col_end = (col_begin + chunk_cols) < row_len ? (col_begin + chunk_cols) : row_len;
+    int4* my = s_quads + warp * k;
+    for (int j = lane; j < k; j += 32) {
+        const int64_t ob = (int64_t)idx[cell * k + j] * row_len * (int64_t)sizeof(float);
+        my[j] = make_int4((int)(uint32_t)ob, (int)(ob >> 32), __float_as_int(w[cell * k + j]), 0);
+    }
+    __syncwarp();
+    const int64_t orow = out_row ? (int64_t)out_row[cell] : cell;
+    Tout* o = out + orow * row_len;
+    constexpr int STEP = 32 * V;
+    for (int64_t col0 = col_begin; col0 < col_end; col0 += (int64_t)STEP * UNROLL) {
+        float acc[UNROLL][V];
+        bool in[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            in[u] = col0 + u * STEP + lane * V < col_end;
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[u][e] = 0.f;
+        }
+        const char* colbase = reinterpret_cast<const char*>(data + col0 + lane * V);
+        for (int j = 0; j < k; ++j) {
+            const int4 q = my[j];
+            const int64_t ob = (int64_t)(((uint64_t)(uint32_t)q.y << 32) | (uint32_t)q.x);
+            const float wj = __int_as_float(q.z);
+            const float* src = reinterpret_cast<const float*>(colbase + ob);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (in[u]) {
+                    const Vec<float, V> x = ld_stream<float, V>(src + u * STEP);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[u][e] = fmaf(wj, x.v[e], acc[u][e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (in[u]) {
+                Vec<Tout, V> ov;
+#pragma unroll
+                for (int e = 0; e < V; ++e) ov.v[e] = (Tout)acc[u][e];
+                *reinterpret_cast<Vec<Tout, V>*>(o + col0 + u * STEP + lane * V) = ov;
+            }
+        }
+    }
+}
+
 // Register-resident variant for the two neighbour counts S^3 uses (k = 8 in 2-D, 26 in 3-D; s_cube.py:161,
 // export.py:117-118): every lane keeps the cell's k (index, weight) pairs in registers (uniform loads, one wavefront
 // each), so the inner loop is address arithmetic + LDG.128 + FFMA only. The shuffle-broadcast of the generic kernel
@@ -485,7 +548,15 @@ static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, 
         reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk)
         const bool sync = g_direct_sync != 0;
         const int g_bcast = s3::g_bcast >= 0 ? s3::g_bcast : (k > 16 ? 2 : 0);      // shadows the knob: resolved per call
-        if (k > 16 && vec_ok && unroll == 2 && !sync && g_direct_window != 0) {
+        if (g_bcast == 4 && vec_ok && !sync && MODE == 0 && std::is_same<Tin, float>::value && std::is_same<Tw, float>::value) {
+            const size_t off_smem = (size_t)warps * k * sizeof(int4);
+            const float* d32 = reinterpret_cast<const float*>(data);
+            const float* w32 = reinterpret_cast<const float*>(w);
+            if (unroll == 2)
+                interp_warpcell_off_kernel<Tout, 4, 2><<<wc_grid, warps * 32, off_smem, stream>>>(d32, row_len, idx, w32, n_cells, k, out_row, out_p, chunk);
+            else
+                interp_warpcell_off_kernel<Tout, 4, 1><<<wc_grid, warps * 32, off_smem, stream>>>(d32, row_len, idx, w32, n_cells, k, out_row, out_p, chunk);
+        } else if (k > 16 && vec_ok && unroll == 2 && !sync && g_direct_window != 0) {
             const size_t pairs_smem = (size_t)warps * ((k + 1) & ~1) * sizeof(int2);
             if (g_bcast == 2 && std::is_same<Tw, float>::value)
                 interp_warpcell_window_kernel<Tin, Tw, Tout, VFULL, MODE, 2, 2><<<wc_grid, warps * 32, pairs_smem, stream>>>(
@@ -600,8 +671,9 @@ extern "C" int s3_set_tuning(int key, int value) {
         s3::g_chunk_cols = value;
         return S3_OK;
     }
+    if (key >= 15 && key <= 18) return s3::set_group_tuning(key, value);
     if (key == 13) {
-        S3_REQUIRE(value >= -1 && value <= 3, "s3_set_tuning: broadcast must be -1 (by k), 0 (SHFL), 1 (REDUX), 2 (LDS.64) or 3 (LDS.128)");
+        S3_REQUIRE(value >= -1 && value <= 4, "s3_set_tuning: broadcast must be -1 (by k), 0 (SHFL), 1 (REDUX), 2 (LDS.64), 3 (LDS.128) or 4 (offset table)");
         s3::g_bcast = value;
         return S3_OK;
     }

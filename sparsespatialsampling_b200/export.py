@@ -15,6 +15,7 @@ Interpolated fields are fp32 by default (fp32 snapshots in, fp32 FMA accumulatio
 reference's fp64 result); ``out_dtype=torch.float64`` reproduces the reference's dtype with fp64 accumulation.
 """
 import logging
+import os
 from os import makedirs, path
 from time import time
 from typing import Union
@@ -24,7 +25,7 @@ import torch as pt
 from . import _lib
 from .const import GRID, CONST, FACES, CENTERS, VERTICES, DATA
 from .data import Datawriter
-from .interpolate import interp_gather, StagedTiles
+from .interpolate import interp_gather, StagedTiles, GroupTables
 from .knn import KnnIndex, default_n_neighbors
 
 logger = logging.getLogger(__name__)
@@ -58,11 +59,25 @@ class KnnTables:
         self.n = q.size(0)
         self.k = k
         self._tiles = None
-        self.mode = "direct"          # "direct" (warp per cell, default) or "staged" (TMA-staged tiles, experimental)
+        self._groups = None
+        self._groups_compact = None
+        # "grouped" (a warp interpolates 4 consecutive cells and loads their distinct rows once), "direct" (warp per
+        # cell) or "staged" / "pipe" (TMA-staged tiles, experimental)
+        self.mode = self.default_mode
         self.chunk_cols = 256
         self.stage_rows = 0
         self.n_ctas = 0
         self.gather4 = True
+
+    # S3B200_INTERP_MODE selects the interpolation kernel of every KnnTables object (A/B runs): direct | grouped
+    default_mode = os.environ.get("S3B200_INTERP_MODE", "direct")
+
+    @property
+    def groups(self) -> GroupTables:
+        """Tables of the grouped kernel, built on first use."""
+        if self._groups is None:
+            self._groups = GroupTables(self.idx_sorted, self.w32_sorted)
+        return self._groups
 
     @property
     def tiles(self):
@@ -80,6 +95,9 @@ class KnnTables:
             return self.tiles.interpolate(data, out=out, out_row=self.out_row, chunk_cols=self.chunk_cols,
                                           pipelined=self.mode == "pipe", stage_rows=self.stage_rows,
                                           n_ctas=self.n_ctas, gather4=self.gather4)
+        if (self.mode == "grouped" and out_dtype == pt.float32 and data.dtype == pt.float32 and row_len % 4 == 0 and
+                data.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0):
+            return self.groups.interpolate(data, out=out, out_row=self.out_row)
         w = self.w32_sorted if out_dtype == pt.float32 else self.w64_sorted
         return interp_gather(data, self.idx_sorted, w, out=out, out_row=self.out_row, out_dtype=out_dtype)
 
@@ -201,7 +219,11 @@ class KnnTables:
                 compute.wait_event(ev_in[c])
                 if c >= 2:
                     compute.wait_event(ev_out[c - 2])         # the copy that drained this output buffer is done
-                if gather:
+                if gather and self.mode == "grouped" and tc % 4 == 0:
+                    if self._groups_compact is None:
+                        self._groups_compact = GroupTables(idx_compact, self.w32_sorted)
+                    self._groups_compact.interpolate(inp, out=res, out_row=self.out_row)
+                elif gather:
                     interp_gather(inp, idx_compact, self.w32_sorted, out=res, out_row=self.out_row, out_dtype=pt.float32)
                 else:
                     self.interpolate(inp, pt.float32, out=res)
@@ -229,6 +251,8 @@ class KnnTables:
         from .parallel import broadcast_tensors
         broadcast_tensors([self.idx_sorted, self.w32_sorted, self.w64_sorted, self.out_row, self.idx, self.w64], src)
         self._tiles = None
+        self._groups = None
+        self._groups_compact = None
         self._rows_unique = None
         return self
 

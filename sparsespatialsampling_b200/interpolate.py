@@ -68,6 +68,52 @@ def interpolate_data(weights: pt.Tensor, idx_weights: pt.Tensor, data: pt.Tensor
     return out if src_device.type == "cuda" else out.to(src_device)
 
 
+class GroupTables:
+    """
+    Tables of the grouped interpolation kernel (``s3_interp_groups_build`` / ``s3_interp_grouped``): for every group of
+    consecutive cells (processing order; group size ``s3_interp_group_size()`` = 4) the distinct source rows of the
+    group, a membership mask and one weight per (row, cell). Built once per KNN cache; a warp then loads every distinct
+    row once for all cells of its group instead of once per (cell, neighbour) reference.
+    """
+
+    def __init__(self, idx_sorted: pt.Tensor, w32_sorted: pt.Tensor):
+        _lib.require_cuda()
+        lib = _lib.load()
+        dev = idx_sorted.device
+        assert idx_sorted.dtype == pt.int32 and w32_sorted.dtype == pt.float32
+        self.n_cells, self.k = idx_sorted.shape
+        self.group = int(lib.s3_interp_group_size())
+        self.n_groups = (self.n_cells + self.group - 1) // self.group
+        cap = self.group * self.k
+        self.cnt = pt.zeros((max(self.n_groups, 1),), dtype=pt.int32, device=dev)
+        self.ent = pt.empty((max(self.n_groups, 1), cap, 2), dtype=pt.int32, device=dev)
+        self.wts = pt.empty((max(self.n_groups, 1), cap, 4), dtype=pt.float32, device=dev)
+        with pt.cuda.device(dev):
+            _lib.check(lib.s3_interp_groups_build(_lib.ptr(idx_sorted.contiguous()), _lib.ptr(w32_sorted.contiguous()),
+                                                  self.n_cells, self.k, _lib.ptr(self.cnt), _lib.ptr(self.ent),
+                                                  _lib.ptr(self.wts), _lib.stream_ptr()))
+
+    @property
+    def rows_per_cell(self) -> float:
+        """Distinct rows loaded per cell (k without grouping)."""
+        return float(self.cnt.sum().item()) / max(self.n_cells, 1)
+
+    def interpolate(self, data: pt.Tensor, out: pt.Tensor = None, out_row: pt.Tensor = None) -> pt.Tensor:
+        lib = _lib.load()
+        assert data.is_cuda and data.dtype == pt.float32
+        data = data.contiguous()
+        n_src = data.size(0)
+        row_len = data.numel() // max(n_src, 1)
+        if out is None:
+            out = pt.empty((self.n_cells,) + tuple(data.shape[1:]), dtype=pt.float32, device=data.device)
+        assert out.is_contiguous() and out.dtype == pt.float32
+        with pt.cuda.device(data.device):
+            _lib.check(lib.s3_interp_grouped(_lib.ptr(data), n_src, row_len, _lib.ptr(self.cnt), _lib.ptr(self.ent),
+                                             _lib.ptr(self.wts), self.n_cells, self.k, _lib.ptr(out_row), _lib.ptr(out),
+                                             _lib.S3_F32, _lib.stream_ptr()))
+        return out
+
+
 class StagedTiles:
     """
     Tile structures of the staged interpolation kernel (``s3_interp_tiles_build`` / ``s3_interp_staged``): for every

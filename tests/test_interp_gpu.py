@@ -165,3 +165,83 @@ def test_export_data_streams_host_batches(cuda, tmp_path):
         exp.export(x, data, "U")
         outs.append(exp.interpolated_fields.centers)
     assert not outs[0].is_cuda and outs[1].is_cuda and pt.equal(outs[0], outs[1].cpu())
+
+
+def _local_case(N, Nc, k, D, T, seed):
+    """Neighbouring cells share neighbours (like Morton-ordered cells of a real grid): idx from a sliding window."""
+    rng = np.random.default_rng(seed)
+    data = rng.standard_normal((N, D, T)).astype(np.float32)
+    base = np.sort(rng.integers(0, max(N - 3 * k, 1), Nc))
+    idx = np.stack([rng.permutation(3 * k)[:k] + b for b in base]).astype(np.int32)   # distinct per cell
+    w = rng.random((Nc, k))
+    w /= w.sum(1, keepdims=True)
+    return data, idx, w
+
+
+@pytest.mark.parametrize("N,Nc,k,D,T", [
+    (5000, 1777, 8, 1, 1000), (5000, 1002, 8, 2, 500), (3000, 515, 26, 3, 64), (2000, 101, 8, 1, 300),
+    (2000, 33, 26, 1, 8), (100, 1, 8, 1, 4), (4000, 2049, 5, 1, 128), (3000, 64, 64, 1, 256),
+])
+def test_grouped_kernel_within_tolerance(cuda, N, Nc, k, D, T):
+    # s3_interp_grouped: a warp interpolates 4 consecutive cells and loads the distinct rows of the group once
+    from sparsespatialsampling_b200.interpolate import GroupTables, interp_gather
+    data, idx, w = _local_case(N, Nc, k, D, T, N + Nc + k)
+    ref = orc.interpolate(w, idx.astype(np.int64), data)
+    d_data, d_idx, d_w = pt.from_numpy(data).cuda(), pt.from_numpy(idx).cuda(), pt.from_numpy(w).float().cuda()
+    groups = GroupTables(d_idx, d_w)
+    assert groups.rows_per_cell <= k
+    if Nc >= 100:
+        assert groups.rows_per_cell < 0.9 * k                   # the sliding-window case does share rows
+    perm = pt.randperm(Nc, device="cuda").to(pt.int32)
+    out = groups.interpolate(d_data, out_row=perm)
+    assert out.dtype == pt.float32 and tuple(out.shape) == (Nc, D, T)
+    got = out.cpu().numpy().astype(np.float64)[perm.cpu().numpy().astype(np.int64)]     # row perm[c] holds cell c
+    scale = np.abs(data[idx]).max(axis=1)
+    err = np.abs(got - ref)
+    assert (err <= RTOL_F32 * np.maximum(scale, 1e-30)).all(), err.max()
+    direct = interp_gather(d_data, d_idx, d_w).cpu().numpy().astype(np.float64)
+    assert (np.abs(got - direct) <= 2 * RTOL_F32 * np.maximum(scale, 1e-30)).all()
+
+
+def test_grouped_kernel_does_not_leak_rows_between_cells(cuda):
+    # a non-finite value in a row used by ONE cell of a group must not reach the other cells of the group, and a row
+    # listed twice for one cell contributes with the sum of its weights
+    from sparsespatialsampling_b200.interpolate import GroupTables
+    N, k, T = 64, 8, 128
+    rng = np.random.default_rng(3)
+    data = rng.standard_normal((N, 1, T)).astype(np.float32)
+    idx = np.stack([np.arange(8) + 2 * c for c in range(6)]).astype(np.int32)           # cells 0..5, overlapping rows
+    idx[1, 3] = idx[1, 2]                                                             # duplicate neighbour in cell 1
+    w = rng.random((6, k))
+    w /= w.sum(1, keepdims=True)
+    data[0, 0, 5] = np.inf                                                            # row 0: cell 0 only
+    data[1, 0, 9] = np.nan                                                            # row 1: cell 0 only
+    out = GroupTables(pt.from_numpy(idx).cuda(), pt.from_numpy(w).float().cuda()).interpolate(
+        pt.from_numpy(data).cuda()).cpu().numpy()
+    assert np.isinf(out[0, 0, 5]) and np.isnan(out[0, 0, 9])
+    assert np.isfinite(out[1:]).all()
+    ref = orc.interpolate(w, idx.astype(np.int64), data)
+    finite = np.isfinite(ref)
+    assert np.allclose(out[finite], ref[finite], rtol=0, atol=1e-5 * np.abs(data[np.isfinite(data)]).max())
+
+
+def test_knn_tables_grouped_mode_equals_direct_mode(cuda):
+    from sparsespatialsampling_b200.export import KnnTables
+    from sparsespatialsampling_b200.knn import KnnIndex
+    rng = np.random.default_rng(11)
+    pts = pt.from_numpy(rng.random((6000, 2)))
+    centers = pt.from_numpy(rng.random((1501, 2)))
+    tables = KnnTables(KnnIndex(pts.cuda()), centers, 8)
+    data = pt.from_numpy(rng.standard_normal((6000, 2, 200)).astype(np.float32)).cuda()
+    tables.mode = "direct"
+    a = tables.interpolate(data, pt.float32)
+    tables.mode = "grouped"
+    b = tables.interpolate(data, pt.float32)
+    assert tables.groups.rows_per_cell < 8
+    scale = float(data.abs().max())
+    assert float((a - b).abs().max()) <= 2 * RTOL_F32 * scale
+    # streamed host path in grouped mode (DMA and row-gather ingest) against the resident result
+    host = data.cpu().pin_memory()
+    for gather in (False, True):
+        c = tables.interpolate_host(host, chunk_snapshots=64, gather=gather)
+        assert pt.equal(c, b.cpu()), gather
