@@ -249,6 +249,10 @@ int s3_svd_gram(const float* d_a, const float* d_mean, const float* d_vol, int v
  * V[:, :r] / s[:r]                                                                                    */
 int s3_svd_project(const float* d_a, const float* d_mean, const float* d_vs, int64_t m, int64_t t, int r,
                    float* d_u, void* stream);
+/* The same projection on the tensor cores: rows centred, weighted by sqrt(vol) and split into TF32 planes as in
+ * s3_svd_gram, contracted with d_vs over t by tcgen05 MMAs (method 1 = 3xTF32, 2 = TF32), un-weighted in the epilogue. */
+int s3_svd_project_tc(const float* d_a, const float* d_mean, const float* d_vol, int vol_div, const float* d_vs,
+                      int64_t m, int64_t t, int r, int method, float* d_u, void* stream);
 
 #ifdef __cplusplus
 }

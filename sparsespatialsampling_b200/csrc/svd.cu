@@ -18,6 +18,10 @@
 //     that halves the L2 -> SM operand traffic but measured the same speed (6.72 vs 6.74 ms): the kernel is bound
 //     by the tensor pipe + TMEM drains, not by operand traffic.
 //   method 0: fp32 CUDA-core tiles (kept as the on-device cross-check of the tensor-core path).
+// Projection U = (A - mean) V / s, 2*M*T*r flop: the same planes contracted over t on tcgen05 (project_tc_kernel, K-major
+//   TF32 operands, 3xTF32, a few TMEM segments against accumulation drift), 262144 x 2000 rows onto r = 50 / 150 / 256
+//   modes in 1.8 / 2.3 / 2.6 ms (of which 1.1 ms is the prepare pass) instead of 4.2 / 12.2 / 16.0 ms on the fp32
+//   CUDA-core kernel, max error vs fp64 2e-6 .. 8e-6 of the largest entry.
 #include <cuda.h>
 #include "common.cuh"
 #include "tma.cuh"
@@ -570,6 +574,183 @@ gram_tc_reduce_kernel(const double* __restrict__ partial, int splits, int n_i, i
     g[e] = acc;
 }
 
+// ================================================================== tensor-core projection
+//   U[m][j] = (1 / sqrt(vol_m)) * sum_t B[m][t] * W[t][j],   B = sqrt(vol) (A - mean) (the planes of the Gram kernel),
+//   W = V / s  [T, r]
+// Here the contraction runs over t, which is the contiguous direction of the planes ([T/32][rows][32]): a TMA box of
+// {32 t, 128 rows} written with the plain 128B swizzle is the canonical K-major UMMA tile (8-row x 128-byte atoms,
+// SBO = 1024), and W is passed transposed ([r_pad][T_pad], t contiguous) so that it is K-major as well. One CTA per
+// 128 rows: warp 0 = TMA producer, warp 1 = MMA issuer (3xTF32: B_l W_h + B_h W_l + B_h W_h), warps 2..5 = epilogue
+// (tcgen05.ld, scale by 1/sqrt(vol), store the r columns of the row). Accumulator: 128 lanes x r_pad TMEM columns.
+constexpr int kPjBM = 128;
+constexpr int kPjStages = 2;
+constexpr int kPjThreads = 6 * 32;
+constexpr int kPjABytes = kPjBM * 128;                       // one plane tile: 128 rows x 32 floats
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major TF32 operand, 128B swizzle: rows of 32 K-contiguous floats, 8-row atoms of 1024 bytes (SBO), LBO unused
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                      // LBO (ignored for swizzled K-major layouts)
+    d |= (uint64_t)(1024 >> 4) << 32;            // SBO
+    d |= (uint64_t)1 << 46;                      // descriptor version 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                      // layout type SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D fp32, A/B TF32, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_k(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// W^T planes: wt[j][tt] = tf32 split of vs[tt][col0 + j] (zero beyond r / t), [r_pad][t_pad]
+__global__ void __launch_bounds__(256)
+project_prepare_w_kernel(const float* __restrict__ vs, int64_t t, int r, int col0, int r_pad, int64_t t_pad,
+                         float* __restrict__ hi, float* __restrict__ lo) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)r_pad * t_pad) return;
+    const int j = (int)(e / t_pad);
+    const int64_t tt = e % t_pad;
+    float w = 0.f;
+    if (col0 + j < r && tt < t) w = vs[tt * r + col0 + j];
+    uint32_t hbits;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hbits) : "f"(w));
+    const float h = __uint_as_float(hbits);
+    hi[e] = h;
+    if (lo) lo[e] = w - h;
+}
+
+__global__ void __launch_bounds__(kPjThreads, 1)
+project_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                  const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo, int n_groups,
+                  int r_pad, int tmem_cols, int n_seg, int passes, const float* __restrict__ vol, int vol_div, int64_t row0,
+                  int64_t m, int r, int col0, float* __restrict__ u) {
+    extern __shared__ __align__(1024) unsigned char pj_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kPjStages];
+    __shared__ __align__(8) uint64_t empty_bar[kPjStages];
+    __shared__ __align__(8) uint64_t acc_bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t raw = smem_u32(pj_smem_raw);
+    const uint32_t ring = (raw + 1023u) & ~1023u;
+    unsigned char* ring_ptr = pj_smem_raw + (ring - raw);
+    const uint32_t w_bytes = (uint32_t)r_pad * 128u;                  // one W^T tile: r_pad rows x 32 floats
+    const uint32_t stage_bytes = 2u * kPjABytes + 2u * w_bytes;       // [B_hi][B_lo][W_hi][W_lo]
+    const int tile_row = blockIdx.x * kPjBM;                          // first plane row of this CTA
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPjStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_bar, 1);
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whi) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx = passes == 3 ? stage_bytes : (kPjABytes + w_bytes);
+            for (int g = 0; g < n_groups; ++g) {
+                const int s = g % kPjStages;
+                const uint32_t round = (uint32_t)(g / kPjStages);
+                if (round > 0) mbar_wait_wd(&empty_bar[s], (round - 1) & 1u);
+                unsigned char* st = ring_ptr + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full_bar[s], tx);
+                tma_load_3d(st, &map_hi, 0, tile_row, g, &full_bar[s]);
+                tma_load_2d(st + 2 * kPjABytes, &map_whi, g * 32, 0, &full_bar[s]);
+                if (passes == 3) {
+                    tma_load_3d(st + kPjABytes, &map_lo, 0, tile_row, g, &full_bar[s]);
+                    tma_load_2d(st + 2 * kPjABytes + w_bytes, &map_wlo, g * 32, 0, &full_bar[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32_k(kPjBM, r_pad);
+            // The tensor core's fp32 accumulation truncates, so the error grows with the length of the chain: the t
+            // range is cut into n_seg segments with their own TMEM columns, summed (round to nearest) in the epilogue.
+            const int per_seg = (n_groups + n_seg - 1) / n_seg;
+            uint32_t accumulate = 0;
+            for (int g = 0; g < n_groups; ++g) {
+                const int s = g % kPjStages;
+                mbar_wait_wd(&full_bar[s], (uint32_t)(g / kPjStages) & 1u);
+                tc_fence_after();
+                const uint32_t st = ring + (uint32_t)s * stage_bytes;
+                const uint32_t d_tmem = tmem_base + (uint32_t)((g / per_seg) * r_pad);
+                if (g % per_seg == 0) accumulate = 0;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {                      // 32 floats per stage = 4 UMMA K-steps of 8
+                    const uint32_t koff = (uint32_t)ks * 32u;
+                    const uint64_t a_hi = umma_desc_k_sw128(st + koff);
+                    const uint64_t b_hi = umma_desc_k_sw128(st + 2 * kPjABytes + koff);
+                    if (passes == 3) {
+                        const uint64_t a_lo = umma_desc_k_sw128(st + kPjABytes + koff);
+                        const uint64_t b_lo = umma_desc_k_sw128(st + 2 * kPjABytes + w_bytes + koff);
+                        umma_tf32(d_tmem, a_lo, b_hi, idesc, accumulate);
+                        umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                        umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                    } else {
+                        umma_tf32(d_tmem, a_hi, b_hi, idesc, accumulate);
+                    }
+                    accumulate = 1u;
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&acc_bar);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;                                       // TMEM lane quarter of this warp
+        const int64_t row = row0 + tile_row + q * 32 + lane;
+        mbar_wait_wd(&acc_bar, 0);
+        tc_fence_after();
+        const float scale = row < m ? rsqrtf(vol[row / vol_div]) : 0.f;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int per_seg = (n_groups + n_seg - 1) / n_seg;
+        const int used_seg = (n_groups + per_seg - 1) / per_seg;      // segments that received at least one stage
+        for (int c0 = 0; c0 < r_pad; c0 += 32) {
+            float acc[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+            for (int sg = 0; sg < used_seg; ++sg) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(sg * r_pad + c0), v);    // warp-collective: all lanes, also dead rows
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[c] = __fadd_rn(acc[c], __uint_as_float(v[c]));
+            }
+            if (row < m) {
+                float* o = u + row * r + col0 + c0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (col0 + c0 + c < r) o[c] = acc[c] * scale;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols)
+                     : "memory");
+    }
+}
+
 }  // namespace s3
 
 using namespace s3;
@@ -726,4 +907,102 @@ extern "C" int s3_svd_project(const float* d_a, const float* d_mean, const float
     S3_LAUNCH_CHECK();
     note_launch(1);
     return S3_OK;
+}
+
+// U = (A - mean) vs on the tensor cores (see project_tc_kernel); vs [t, r] fp32, u [m, r] fp32.
+static int project_tc(const float* d_a, const float* d_mean, const float* d_vol, int vol_div, const float* d_vs,
+                      int64_t m, int64_t t, int r, int passes, float* d_u, cudaStream_t st) {
+    static PFN_encodeTiledSvd encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        S3_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        S3_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+        encode = (PFN_encodeTiledSvd)fn;
+    }
+    const int64_t t_pad = ceil_div(t, (int64_t)32) * 32;
+    const int n_groups = (int)(t_pad / 32);
+    // rows of A per chunk: each plane at most 2 GB, a multiple of the 128-row tile
+    int64_t plane_rows = ((int64_t)(1ll << 31) / (t_pad * 4)) & ~(int64_t)(kPjBM - 1);
+    if (plane_rows < kPjBM) plane_rows = kPjBM;
+    const int64_t m_pad = ceil_div(m, (int64_t)kPjBM) * kPjBM;
+    if (plane_rows > m_pad) plane_rows = m_pad;
+    const int r_blk_max = r < 256 ? (int)(ceil_div((int64_t)r, (int64_t)32) * 32) : 256;   // columns per pass, multiple of 32
+
+    Scratch scratch(st);
+    float *hi = nullptr, *lo = nullptr, *whi = nullptr, *wlo = nullptr;
+    S3_TRY(scratch.alloc(&hi, (size_t)plane_rows * t_pad));
+    if (passes == 3) S3_TRY(scratch.alloc(&lo, (size_t)plane_rows * t_pad));
+    S3_TRY(scratch.alloc(&whi, (size_t)r_blk_max * t_pad));
+    if (passes == 3) S3_TRY(scratch.alloc(&wlo, (size_t)r_blk_max * t_pad));
+
+    CUtensorMap map_hi, map_lo;
+    memset(&map_hi, 0, sizeof(map_hi));
+    memset(&map_lo, 0, sizeof(map_lo));
+    {
+        const cuuint64_t gdim[3] = {32, (cuuint64_t)plane_rows, (cuuint64_t)n_groups};
+        const cuuint64_t gstride[2] = {128, (cuuint64_t)plane_rows * 128};
+        const cuuint32_t box[3] = {32, (cuuint32_t)kPjBM, 1};
+        const cuuint32_t estride[3] = {1, 1, 1};
+        CUresult cr = encode(&map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, hi, gdim, gstride, box, estride,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        S3_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(projection hi) failed with code %d", (int)cr);
+        cr = encode(&map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, passes == 3 ? lo : hi, gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        S3_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(projection lo) failed with code %d", (int)cr);
+    }
+    for (int col0 = 0; col0 < r; col0 += 256) {
+        const int r_blk = (r - col0) < 256 ? (r - col0) : 256;
+        const int r_pad = (int)(ceil_div((int64_t)r_blk, (int64_t)32) * 32);
+        // TMEM: up to 256 columns (two CTAs may share an SM), 512 when the stages leave room for one CTA only
+        const int tmem_cols = r_pad > 128 ? 512 : 256;
+        int n_seg = tmem_cols / r_pad;
+        if (n_seg > 8) n_seg = 8;
+        if (n_seg > n_groups) n_seg = n_groups;
+        project_prepare_w_kernel<<<(unsigned)ceil_div((int64_t)r_pad * t_pad, (int64_t)256), 256, 0, st>>>(
+            d_vs, t, r, col0, r_pad, t_pad, whi, wlo);
+        CUtensorMap map_whi, map_wlo;
+        memset(&map_whi, 0, sizeof(map_whi));
+        memset(&map_wlo, 0, sizeof(map_wlo));
+        {
+            const cuuint64_t gdim[2] = {(cuuint64_t)t_pad, (cuuint64_t)r_pad};
+            const cuuint64_t gstride[1] = {(cuuint64_t)t_pad * 4};
+            const cuuint32_t box[2] = {32, (cuuint32_t)r_pad};
+            const cuuint32_t estride[2] = {1, 1};
+            CUresult cr = encode(&map_whi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, whi, gdim, gstride, box, estride,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            S3_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(projection W hi) failed with code %d", (int)cr);
+            cr = encode(&map_wlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, passes == 3 ? wlo : whi, gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            S3_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(projection W lo) failed with code %d", (int)cr);
+        }
+        const size_t smem = (size_t)kPjStages * (2 * kPjABytes + 2 * (size_t)r_pad * 128) + 1024;
+        S3_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int64_t row0 = 0; row0 < m; row0 += plane_rows) {
+            const int64_t rows = (m - row0) < plane_rows ? (m - row0) : plane_rows;
+            const int64_t rows_pad = ceil_div(rows, (int64_t)kPjBM) * kPjBM;
+            gram_prepare_kernel<<<(unsigned)ceil_div(rows_pad * 32, (int64_t)256), 256, 0, st>>>(
+                d_a, d_mean, d_vol, vol_div, row0, rows_pad, m, t, n_groups, plane_rows, hi, lo);
+            project_tc_kernel<<<(unsigned)(rows_pad / kPjBM), kPjThreads, smem, st>>>(
+                map_hi, map_lo, map_whi, map_wlo, n_groups, r_pad, tmem_cols, n_seg, passes, d_vol, vol_div, row0, m, r,
+                col0, d_u);
+            S3_LAUNCH_CHECK();
+            note_launch(2);
+        }
+        note_launch(1);
+    }
+    return S3_OK;
+}
+
+extern "C" int s3_svd_project_tc(const float* d_a, const float* d_mean, const float* d_vol, int vol_div,
+                                 const float* d_vs, int64_t m, int64_t t, int r, int method, float* d_u, void* stream) {
+    S3_REQUIRE(d_a && d_mean && d_vol && d_vs && d_u, "s3_svd_project_tc: NULL argument");
+    S3_REQUIRE(m >= 0 && t >= 1 && r >= 1 && vol_div >= 1, "s3_svd_project_tc: bad sizes");
+    S3_REQUIRE(method == 1 || method == 2, "s3_svd_project_tc: method must be 1 (3xTF32) or 2 (TF32)");
+    if (m == 0) return S3_OK;
+    return project_tc(d_a, d_mean, d_vol, vol_div, d_vs, m, t, r, method == 1 ? 3 : 1, d_u, (cudaStream_t)stream);
 }

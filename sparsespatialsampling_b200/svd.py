@@ -81,6 +81,19 @@ def project(a: pt.Tensor, mean: pt.Tensor, vs: pt.Tensor) -> pt.Tensor:
     return u
 
 
+def project_tc(a: pt.Tensor, mean: pt.Tensor, vol: pt.Tensor, vol_div: int, vs: pt.Tensor, method: str = "tc3") -> pt.Tensor:
+    """The same projection on the tensor cores (``s3_svd_project_tc``): the rows are centred, weighted and split into
+    TF32 planes exactly as for the Gram matrix, contracted with ``vs`` over t by tcgen05 MMAs (3xTF32 for ``"tc3"``)
+    and un-weighted in the epilogue. fp32 [M, r]."""
+    lib = _lib.load()
+    vs = vs.to(pt.float32).contiguous()
+    u = pt.empty((a.size(0), vs.size(1)), dtype=pt.float32, device=a.device)
+    with pt.cuda.device(a.device):
+        _lib.check(lib.s3_svd_project_tc(_lib.ptr(a), _lib.ptr(mean), _lib.ptr(vol), vol_div, _lib.ptr(vs), a.size(0),
+                                         a.size(1), vs.size(1), GRAM_METHODS[method], _lib.ptr(u), _lib.stream_ptr()))
+    return u
+
+
 def compute_svd(data_matrix: pt.Tensor, cell_area: pt.Tensor, rank: int = None, method: str = "tc3",
                 n_modes: int = None, device=None) -> Tuple[pt.Tensor, pt.Tensor, pt.Tensor]:
     """
@@ -111,7 +124,7 @@ def compute_svd(data_matrix: pt.Tensor, cell_area: pt.Tensor, rank: int = None, 
 
     mean = row_means(a)
     g = gram(a, mean, vol, vol_div, method)
-    s_out, u, v_out = _factor(a, mean, g, rank, n_modes, a.size(0))
+    s_out, u, v_out = _factor(a, mean, g, rank, n_modes, a.size(0), vol, vol_div, method)
     if len(shape) == 3:
         u = u.reshape(n_cells, vol_div, u.size(-1))
     if home != dev:
@@ -120,7 +133,8 @@ def compute_svd(data_matrix: pt.Tensor, cell_area: pt.Tensor, rank: int = None, 
     return s_out, u, v_out
 
 
-def _factor(a: pt.Tensor, mean: pt.Tensor, g: pt.Tensor, rank, n_modes, rows_total: int):
+def _factor(a: pt.Tensor, mean: pt.Tensor, g: pt.Tensor, rank, n_modes, rows_total: int, vol: pt.Tensor, vol_div: int,
+            method: str):
     """Eigen-decomposition of the (summed) Gram matrix and projection of the rows held in ``a``."""
     t = a.size(1)
     lam, vec = pt.linalg.eigh(g)                       # ascending, fp64
@@ -137,7 +151,8 @@ def _factor(a: pt.Tensor, mean: pt.Tensor, g: pt.Tensor, rank, n_modes, rows_tot
     r_u = r if n_modes is None else max(1, min(int(n_modes), r))
     live = s[:r_u] > 1e-6 * float(s_all[0]) if float(s_all[0]) > 0 else pt.zeros(r_u, dtype=pt.bool, device=a.device)
     inv_s = pt.where(live, 1.0 / s[:r_u].clamp_min(1e-300), pt.zeros_like(s[:r_u]))
-    u = project(a, mean, v[:, :r_u] * inv_s.unsqueeze(0))
+    vs = v[:, :r_u] * inv_s.unsqueeze(0)
+    u = project(a, mean, vs) if method == "simt" else project_tc(a, mean, vol, vol_div, vs, method)
     return s.to(pt.float32), u, v.to(pt.float32)
 
 
@@ -196,7 +211,7 @@ def compute_svd_sharded(data_local: pt.Tensor, cell_area_local: pt.Tensor, rank:
     parallel.allreduce_sum(g, group)
     parallel.allreduce_sum(counts, group)
     rows_total = int(counts.item())
-    s_out, u, v_out = _factor(a, mean, g, rank, n_modes, rows_total)
+    s_out, u, v_out = _factor(a, mean, g, rank, n_modes, rows_total, vol, vol_div, method)
     if len(shape) == 3:
         u = u.reshape(n_local, vol_div, u.size(-1))
     if gather_modes:

@@ -147,3 +147,24 @@ def test_write_svd_s_cube_to_file(cuda, tmp_path):
         assert st.read("constant/mode_1").shape == ((1535,) if name == "p" else (1535, 2))
         xdmf = open(tmp_path / f"case_{name}_svd.xdmf").read()
         assert 'Attribute Name="mode_3"' in xdmf and 'Attribute Name="cell_area"' in xdmf and "Name=\"V\"" not in xdmf
+
+
+@pytest.mark.parametrize("m,t,r,vol_div", [(1000, 96, 7, 1), (5003, 301, 40, 1), (3000, 200, 300, 2), (129, 33, 1, 1),
+                                           (70000, 1000, 50, 1)])
+def test_tensor_core_projection_matches_fp64(cuda, m, t, r, vol_div):
+    # s3_svd_project_tc: U = (A - mean) W with the contraction over t on tcgen05 (K-major TF32 operands)
+    from sparsespatialsampling_b200 import svd
+    g = pt.Generator(device="cuda").manual_seed(m + r)
+    a = pt.randn((m, t), device="cuda", generator=g) + 3.0                 # a mean well away from zero
+    vol = pt.rand((m // vol_div,), device="cuda", generator=g) + 0.5
+    w = pt.randn((t, r), device="cuda", generator=g)
+    mean = svd.row_means(a)
+    ref = (a.double() - mean.double()[:, None]) @ w.double()
+    scale = float(ref.abs().max())
+    u3 = svd.project_tc(a, mean, vol, vol_div, w, "tc3")
+    assert tuple(u3.shape) == (m, r) and u3.dtype == pt.float32
+    assert float((u3.double() - ref).abs().max()) <= 2e-5 * scale           # 3xTF32 ~ fp32 accuracy
+    u1 = svd.project_tc(a, mean, vol, vol_div, w, "tc")
+    assert float((u1.double() - ref).abs().max()) <= 5e-3 * scale           # single TF32 pass
+    us = svd.project(a, mean, w)                                            # fp32 CUDA-core kernel
+    assert float((us.double() - ref).abs().max()) <= 2e-5 * scale
