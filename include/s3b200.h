@@ -40,7 +40,7 @@ int64_t s3_launch_count(void);
  * key 10 = 16-row K-blocks accumulated in TMEM per segment of the tensor-core Gram kernel (default 8),
  * key 11 = segments summed in fp32 registers per fp64 flush (default 128), key 13 = how a warp of the interpolation
  * kernel broadcasts a cell's (index, weight) pairs: -1 by k (default), 0 SHFL, 1 REDUX, 2 / 3 shared memory,
- * 4 byte-offset table; keys 15-18 = grouped kernel: warps per CTA, distinct rows in flight per lane (1, 2, 3, 4, 6,
+ * 4 byte-offset table, 52 / 53 / 54 / 58 the same with fenced batches of 2 / 3 / 4 / 8 row loads; keys 15-18 = grouped kernel: warps per CTA, distinct rows in flight per lane (1, 2, 3, 4, 6,
  * 8), CTAs per SM the register allocation must allow (2..6), column vectors per lane (1, 2),
  * key 14 = Gram kernel in clusters of two CTAs that share the B operand by TMA multicast (default 1) */
 int s3_set_tuning(int key, int value);

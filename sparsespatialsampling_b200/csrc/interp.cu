@@ -436,6 +436,68 @@ interp_warpcell_off_kernel(const float* __restrict__ data, int64_t row_len, cons
     }
 }
 
+// Fenced-batch variant of the offset-table kernel: BATCH neighbour rows are loaded (ordinary global loads) BEFORE a warp
+// barrier and the weights are read from shared memory AFTER it, which pins the memory-level parallelism per warp to
+// BATCH whatever ptxas would schedule (it otherwise sinks every load next to its first FFMA, interp_group.cu). The
+// table is padded to a multiple of BATCH with the first row at weight 0.
+template <typename Tout, int V, int BATCH>
+__global__ void __launch_bounds__(512)
+interp_warpcell_batch_kernel(const float* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
+                             const float* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
+                             Tout* __restrict__ out, int64_t chunk_cols) {
+    extern __shared__ __align__(16) unsigned char bt_smem[];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t cell = (int64_t)blockIdx.x * warps + warp;
+    if (cell >= n_cells) return;
+    const int k_pad = ((k + BATCH - 1) / BATCH) * BATCH;
+    int64_t* s_off = reinterpret_cast<int64_t*>(bt_smem) + (size_t)warp * k_pad;
+    float* s_w = reinterpret_cast<float*>(bt_smem + (size_t)warps * k_pad * sizeof(int64_t)) + (size_t)warp * k_pad;
+    for (int j = lane; j < k_pad; j += 32) {
+        const int jj = j < k ? j : 0;
+        s_off[j] = (int64_t)idx[cell * k + jj] * row_len * (int64_t)sizeof(float);
+        s_w[j] = j < k ? w[cell * k + j] : 0.f;
+    }
+    __syncwarp();
+    const int64_t col_begin = (int64_t)blockIdx.y * chunk_cols;
+    const int64_t col_end = (col_begin + chunk_cols) < row_len ? (col_begin + chunk_cols) : row_len;
+    const int64_t orow = out_row ? (int64_t)out_row[cell] : cell;
+    Tout* o = out + orow * row_len;
+    constexpr int STEP = 32 * V;
+    for (int64_t col0 = col_begin; col0 < col_end; col0 += STEP) {
+        float acc[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = 0.f;
+        const bool in = col0 + lane * V < col_end;
+        const char* colbase = reinterpret_cast<const char*>(data + (in ? col0 + lane * V : col0));
+        for (int j = 0; j < k_pad; j += BATCH) {
+            float4 x[BATCH];
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(x[b].x), "=f"(x[b].y), "=f"(x[b].z), "=f"(x[b].w)
+                             : "l"(colbase + s_off[j + b])
+                             : "memory");
+            }
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                const float wj = s_w[j + b];
+                acc[0] = fmaf(wj, x[b].x, acc[0]);
+                acc[1] = fmaf(wj, x[b].y, acc[1]);
+                acc[2] = fmaf(wj, x[b].z, acc[2]);
+                acc[3] = fmaf(wj, x[b].w, acc[3]);
+            }
+        }
+        if (in) {
+            Vec<Tout, V> ov;
+#pragma unroll
+            for (int e = 0; e < V; ++e) ov.v[e] = (Tout)acc[e];
+            *reinterpret_cast<Vec<Tout, V>*>(o + col0 + lane * V) = ov;
+        }
+    }
+}
+
 // Register-resident variant for the two neighbour counts S^3 uses (k = 8 in 2-D, 26 in 3-D; s_cube.py:161,
 // export.py:117-118): every lane keeps the cell's k (index, weight) pairs in registers (uniform loads, one wavefront
 // each), so the inner loop is address arithmetic + LDG.128 + FFMA only. The shuffle-broadcast of the generic kernel
@@ -548,7 +610,18 @@ static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, 
         reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk)
         const bool sync = g_direct_sync != 0;
         const int g_bcast = s3::g_bcast >= 0 ? s3::g_bcast : (k > 16 ? 2 : 0);      // shadows the knob: resolved per call
-        if (g_bcast == 4 && vec_ok && !sync && MODE == 0 && std::is_same<Tin, float>::value && std::is_same<Tw, float>::value) {
+        if (g_bcast >= 52 && vec_ok && !sync && MODE == 0 && std::is_same<Tin, float>::value && std::is_same<Tw, float>::value) {
+            const int batch = g_bcast - 50;
+            const int k_pad = ((k + batch - 1) / batch) * batch;
+            const size_t bsmem = (size_t)warps * k_pad * (sizeof(int64_t) + sizeof(float));
+            const float* d32 = reinterpret_cast<const float*>(data);
+            const float* w32 = reinterpret_cast<const float*>(w);
+#define S3_BATCH(BB)                                                                                             \
+    interp_warpcell_batch_kernel<Tout, 4, BB><<<wc_grid, warps * 32, bsmem, stream>>>(d32, row_len, idx, w32, n_cells, \
+                                                                                        k, out_row, out_p, chunk)
+            if (batch == 2) S3_BATCH(2); else if (batch == 8) S3_BATCH(8); else if (batch == 3) S3_BATCH(3); else S3_BATCH(4);
+#undef S3_BATCH
+        } else if (g_bcast == 4 && vec_ok && !sync && MODE == 0 && std::is_same<Tin, float>::value && std::is_same<Tw, float>::value) {
             const size_t off_smem = (size_t)warps * k * sizeof(int4);
             const float* d32 = reinterpret_cast<const float*>(data);
             const float* w32 = reinterpret_cast<const float*>(w);
@@ -673,7 +746,9 @@ extern "C" int s3_set_tuning(int key, int value) {
     }
     if (key >= 15 && key <= 18) return s3::set_group_tuning(key, value);
     if (key == 13) {
-        S3_REQUIRE(value >= -1 && value <= 4, "s3_set_tuning: broadcast must be -1 (by k), 0 (SHFL), 1 (REDUX), 2 (LDS.64), 3 (LDS.128) or 4 (offset table)");
+        S3_REQUIRE((value >= -1 && value <= 4) || value == 52 || value == 53 || value == 54 || value == 58,
+                   "s3_set_tuning: broadcast must be -1 (by k), 0 (SHFL), 1 (REDUX), 2 (LDS.64), 3 (LDS.128), 4 (offset table) or "
+                   "52 / 53 / 54 / 58 (fenced batches of 2 / 3 / 4 / 8 rows)");
         s3::g_bcast = value;
         return S3_OK;
     }
