@@ -92,3 +92,25 @@ def test_svd_exchange_world_size_3(tmp_path):
         g = np.load(tmp_path / f"gram{r}.npy")
         assert np.allclose(g, ref, rtol=1e-12, atol=1e-12)
         assert np.array_equal(g, np.load(tmp_path / "gram0.npy"))
+
+
+def test_bind_to_gpu_numa_node_is_harmless_without_nvml():
+    # no GPU / NVML in the CPU container: the helper must leave the affinity alone and say so
+    from sparsespatialsampling_b200.parallel import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    cores = bind_to_gpu_numa_node(0)
+    assert cores is None or set(cores) <= before
+    if cores is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
+
+
+def test_row_and_snapshot_windows_partition_the_axis():
+    from sparsespatialsampling_b200.parallel import snapshot_window, row_window
+    for n, world in [(1000, 8), (13, 3), (5, 8), (0, 2)]:
+        edges = [snapshot_window(n, world, r) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        sizes = [b - a for a, b in edges]
+        assert max(sizes) - min(sizes) <= 1
+        assert edges == [row_window(n, world, r) for r in range(world)]
