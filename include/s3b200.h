@@ -42,7 +42,8 @@ int64_t s3_launch_count(void);
  * kernel broadcasts a cell's (index, weight) pairs: -1 by k (default), 0 SHFL, 1 REDUX, 2 / 3 shared memory,
  * 4 byte-offset table, 52 / 53 / 54 / 58 the same with fenced batches of 2 / 3 / 4 / 8 row loads; keys 15-18 = grouped kernel: warps per CTA, distinct rows in flight per lane (1, 2, 3, 4, 6,
  * 8), CTAs per SM the register allocation must allow (2..6), column vectors per lane (1, 2),
- * key 14 = Gram kernel in clusters of two CTAs that share the B operand by TMA multicast (default 1) */
+ * key 14 = Gram kernel in clusters of two CTAs that share the B operand by TMA multicast (default 1),
+ * key 20 = shared-memory carve-out (percent) requested for the warp-per-cell kernel, -1 = driver default */
 int s3_set_tuning(int key, int value);
 
 /* ---- k-nearest-neighbour index over the original point cloud ---------------------------------

@@ -31,6 +31,7 @@ static int g_warps_per_cta = 8;
 static int g_direct_regs = 0;      // k = 8 / 26: (idx, w) in registers instead of shuffle broadcasts (s3_set_tuning key 8)
 static int g_bcast = -1;           // (idx, w) broadcast in the warp-per-cell kernels: 0 = SHFL, 1 = REDUX.OR, 2 / 3 = LDS.64 / LDS.128 from
                                    // shared memory, -1 = by k (k > 16: 2, else 0; measured) (s3_set_tuning key 13)
+static int g_carveout = -1;        // shared-memory carve-out (percent) requested for the warp-per-cell kernel, -1 = driver default (s3_set_tuning key 20)
 static int g_direct_window = 1;    // k > 16: window formulation of the warp-per-cell kernel (s3_set_tuning key 12)
 static int g_chunk_cols = 0;       // columns per grid.y window of the warp-per-cell kernel, 0 = by k (s3_set_tuning key 9)
 static int g_direct_sync = 0;      // barrier per column step in the warp-per-cell kernel (s3_set_tuning key 7)
@@ -606,8 +607,13 @@ static int launch_interp(const void* data, int64_t row_len, const int32_t* idx, 
         if (n_chunks > 65535) { chunk = ceil_div(ceil_div(row_len, 65535), 256) * 256; n_chunks = ceil_div(row_len, chunk); }
         const dim3 wc_grid((unsigned)blocks, (unsigned)n_chunks);
 #define S3_WARPCELL(VV, UU, SS, CC)                                                                             \
-    interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, SS, CC><<<wc_grid, warps * 32, 0, stream>>>(               \
-        reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk)
+    do {                                                                                                        \
+        if (g_carveout >= 0)                                                                                    \
+            cudaFuncSetAttribute(interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, SS, CC>,                     \
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);                   \
+        interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, SS, CC><<<wc_grid, warps * 32, 0, stream>>>(           \
+            reinterpret_cast<const Tin*>(data), row_len, idx, w_p, n_cells, k, out_row, out_p, row_len, chunk);  \
+    } while (0)
         const bool sync = g_direct_sync != 0;
         const int g_bcast = s3::g_bcast >= 0 ? s3::g_bcast : (k > 16 ? 2 : 0);      // shadows the knob: resolved per call
         if (g_bcast >= 52 && vec_ok && !sync && MODE == 0 && std::is_same<Tin, float>::value && std::is_same<Tw, float>::value) {
@@ -745,6 +751,11 @@ extern "C" int s3_set_tuning(int key, int value) {
         return S3_OK;
     }
     if (key >= 15 && key <= 18) return s3::set_group_tuning(key, value);
+    if (key == 20) {
+        S3_REQUIRE(value >= -1 && value <= 100, "s3_set_tuning: carve-out must be -1 (default) or 0..100 percent");
+        s3::g_carveout = value;
+        return S3_OK;
+    }
     if (key == 13) {
         S3_REQUIRE((value >= -1 && value <= 4) || value == 52 || value == 53 || value == 54 || value == 58,
                    "s3_set_tuning: broadcast must be -1 (by k), 0 (SHFL), 1 (REDUX), 2 (LDS.64), 3 (LDS.128), 4 (offset table) or "
