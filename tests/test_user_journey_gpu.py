@@ -1,0 +1,78 @@
+"""
+The reference's 2-D cylinder example (examples/s3_for_cylinder2D_Re100.py:42-73) end to end through the public classes,
+on synthetic data: grid generation -> ExportData (p in one call, U in two snapshot batches, one HDF5/XDMF pair) ->
+write_svd_s_cube_to_file -> Dataloader reads fields and modes back. Every stage is cross-checked against the CPU oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch as pt
+
+from oracle import s3_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cylinder2d_example_flow(cuda, tmp_path):
+    import synth
+    import sparsespatialsampling_b200 as s3
+    from sparsespatialsampling_b200 import (SparseSpatialSampling, ExportData, Dataloader, write_svd_s_cube_to_file)
+    from sparsespatialsampling_b200.geometry import CubeGeometry, SphereGeometry
+    n_t = 24
+    coord = synth.cylinder2d_cloud(6000, seed=31)
+    u = synth.wake_field(coord, 0, n_t, n_t, components=2)                 # [N, 2, T] fp32
+    p = synth.wake_field(coord, 0, n_t, n_t, components=1)                 # [N, 1, T]
+    write_times = [f"{0.1 * i:.1f}" for i in range(n_t)]
+    domain = CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"])
+    cylinder = SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"], refine=True,
+                              min_refinement_level=7)
+    metric = pt.mean(u.abs().sum(1), 1).to(pt.float64)
+    s_cube = SparseSpatialSampling(coord, metric, [domain, cylinder], str(tmp_path), "metric_0.60", "cylinder2D",
+                                   uniform_levels=4, min_metric=0.6, n_jobs=4)
+    s_cube.execute_grid_generation()
+    nc = s_cube.centers.size(0)
+    assert nc > 200 and s_cube.faces.shape == (nc, 4)
+
+    # grid: same leaves as the oracle's restatement of the reference loop
+    tree = orc.OracleTree(coord.numpy(), metric.numpy(), [domain, cylinder], uniform_level=4, min_metric=0.6,
+                          sdm_order=1).refine()
+    assert np.array_equal(tree.all_centers, s_cube.centers.numpy())
+    assert np.array_equal(tree.all_levels, s_cube.levels.numpy())
+
+    export = ExportData(s_cube, write_new_file_for_each_field=False, write_times=write_times)
+    export.export(coord, p, "p")
+    export.export(coord, u[:, :, :10], "U", n_snapshots_total=n_t)        # two batches of snapshots
+    export.export(coord, u[:, :, 10:], "U", n_snapshots_total=n_t)
+    export.synchronize() if hasattr(export, "synchronize") else None
+
+    loader = Dataloader(str(tmp_path), "metric_0.60.h5")
+    assert loader.write_times == write_times
+    assert sorted(loader.field_names[write_times[0]]) == ["U", "p"]
+    assert np.array_equal(loader.vertices.numpy(), s_cube.centers.numpy())
+    p_s, u_s = loader.load_snapshot("p"), loader.load_snapshot("U")
+    assert tuple(p_s.shape) == (nc, n_t) and tuple(u_s.shape) == (nc, 2, n_t)
+    # interpolation against the oracle (export.py:403-468)
+    d, idx = orc.knn_search(coord.numpy(), s_cube.centers.numpy(), 8)
+    w = orc.export_weights(d)
+    ref_u = orc.interpolate(w, idx, u.numpy())
+    ref_p = orc.interpolate(w, idx, p.numpy())[:, 0]
+    assert np.abs(u_s.numpy() - ref_u).max() <= 1e-5 * np.abs(u.numpy()).max()
+    assert np.abs(p_s.numpy() - ref_p).max() <= 1e-5 * np.abs(p.numpy()).max()
+    assert os.path.exists(tmp_path / "metric_0.60.xdmf")
+
+    # SVD of both fields from the written file (utils.py:349-413)
+    write_svd_s_cube_to_file(["p", "U"], str(tmp_path), "metric_0.60", export.new_file, 5, rank=int(1e5),
+                             t_start=0.4)
+    keep = [i for i, t in enumerate(write_times) if float(t) >= 0.4]
+    for name, ref_field in (("p", ref_p[:, keep]), ("U", ref_u[:, :, keep])):
+        out = Dataloader(str(tmp_path), f"metric_0.60_{name}_svd.h5")
+        st = out._store()
+        s = np.asarray(st.read("constant/s")).reshape(-1)
+        assert s.shape[0] == len(keep) and np.all(np.diff(s) <= 1e-6 * s[0])
+        s_ref, u_ref, v_ref = orc.compute_svd(ref_field.astype(np.float32), loader.weights.numpy(), len(keep))
+        assert np.abs(s[:5] - s_ref[:5]).max() <= 1e-4 * s_ref[0]
+        mode1 = np.asarray(st.read("constant/mode_1")).reshape(-1)
+        ref1 = np.asarray(u_ref)[..., 0].reshape(-1)
+        assert abs(mode1 @ ref1) / (np.linalg.norm(mode1) * np.linalg.norm(ref1)) >= 1 - 1e-4
+        assert os.path.exists(tmp_path / f"metric_0.60_{name}_svd.xdmf")
