@@ -76,3 +76,50 @@ def test_cylinder2d_example_flow(cuda, tmp_path):
         ref1 = np.asarray(u_ref)[..., 0].reshape(-1)
         assert abs(mode1 @ ref1) / (np.linalg.norm(mode1) * np.linalg.norm(ref1)) >= 1 - 1e-4
         assert os.path.exists(tmp_path / f"metric_0.60_{name}_svd.xdmf")
+
+
+def test_cylinder3d_example_flow_snapshot_wise(cuda, tmp_path):
+    # examples/s3_for_cylinder3D_Re3900.py:106-141: 3-D cloud, CylinderGeometry3D longer than the domain, fields exported
+    # snapshot by snapshot (batch size 1, utils.py:210-226), values at cell centres AND vertices, SVD of the scalar field
+    import synth
+    from sparsespatialsampling_b200 import (SparseSpatialSampling, ExportData, Dataloader, write_svd_s_cube_to_file)
+    from sparsespatialsampling_b200.geometry import CubeGeometry, CylinderGeometry3D
+    n_t = 6
+    coord = synth.cylinder3d_cloud(5000, seed=41)
+    p = synth.wake_field(coord, 0, n_t, n_t, components=1, xc=0.8, yc=1.0)
+    metric = synth.wake_metric(coord, xc=0.8, yc=1.0)
+    write_times = [str(i) for i in range(n_t)]
+    geometry = [CubeGeometry("domain", True, synth.CYL3D["lower"], synth.CYL3D["upper"]),
+                CylinderGeometry3D("cylinder", False, [(0.8, 1.0, -1), (0.8, 1.0, 1)], 0.25, refine=True)]
+    s_cube = SparseSpatialSampling(coord, metric, geometry, str(tmp_path), "c3d_metric_0.50", "cylinder",
+                                   uniform_levels=3, min_metric=0.5, n_jobs=8, max_delta_level=False)
+    s_cube.execute_grid_generation()
+    nc, nv = s_cube.centers.size(0), s_cube.vertices.size(0)
+    assert s_cube.faces.shape == (nc, 8) and int(s_cube.faces.max()) == nv - 1
+    tree = orc.OracleTree(coord.numpy(), metric.numpy(), geometry, uniform_level=3, min_metric=0.5, sdm_order=1).refine()
+    assert np.array_equal(tree.all_centers, s_cube.centers.numpy())
+
+    export = ExportData(s_cube, interpolate_at_vertices=True, write_times=write_times)
+    for i in range(n_t):                                                  # batch size 1
+        export.export(coord, p[:, :, i:i + 1], "p", n_snapshots_total=n_t)
+    loader = Dataloader(str(tmp_path), "c3d_metric_0.50.h5")
+    assert loader.write_times == write_times
+    p_s = loader.load_snapshot("p")
+    assert tuple(p_s.shape) == (nc, n_t)
+    d, idx = orc.knn_search(coord.numpy(), s_cube.centers.numpy(), 26)
+    ref_p = orc.interpolate(orc.export_weights(d), idx, p.numpy())[:, 0]
+    assert np.abs(p_s.numpy() - ref_p).max() <= 1e-5 * np.abs(p.numpy()).max()
+    # the same field at the vertices of the grid (export.py:226-228, 437-444)
+    st = loader._store()
+    at_vertices = np.stack([np.asarray(st.read(f"data/{t}/p_vertices")).reshape(-1) for t in write_times], axis=1)
+    dv, iv = orc.knn_search(coord.numpy(), s_cube.vertices.numpy(), 26)
+    ref_v = orc.interpolate(orc.export_weights(dv), iv, p.numpy())[:, 0]
+    assert at_vertices.shape == (nv, n_t)
+    assert np.abs(at_vertices - ref_v).max() <= 1e-5 * np.abs(p.numpy()).max()
+
+    write_svd_s_cube_to_file(["p"], str(tmp_path), "c3d_metric_0.50", export.new_file, 3, rank=int(1e5))
+    out = Dataloader(str(tmp_path), "c3d_metric_0.50_p_svd.h5")._store()
+    s = np.asarray(out.read("constant/s")).reshape(-1)
+    s_ref, u_ref, _ = orc.compute_svd(ref_p.astype(np.float32), loader.weights.numpy(), n_t)
+    assert s.shape[0] == n_t and np.abs(s[:3] - s_ref[:3]).max() <= 1e-4 * s_ref[0]
+    assert sorted(k for k in out.keys("constant") if k.startswith("mode_")) == ["mode_1", "mode_2", "mode_3"]
