@@ -123,3 +123,57 @@ def test_cylinder3d_example_flow_snapshot_wise(cuda, tmp_path):
     s_ref, u_ref, _ = orc.compute_svd(ref_p.astype(np.float32), loader.weights.numpy(), n_t)
     assert s.shape[0] == n_t and np.abs(s[:3] - s_ref[:3]).max() <= 1e-4 * s_ref[0]
     assert sorted(k for k in out.keys("constant") if k.startswith("mode_")) == ["mode_1", "mode_2", "mode_3"]
+
+
+def test_oat15_example_flow_polygon_bodies(cuda, tmp_path):
+    # examples/s3_for_OAT15_airfoil.py:100-133: two bodies given as closed coordinate rings (GeometryCoordinates2D),
+    # write times passed as floats, a scalar field [N, T] unsqueezed to [N, 1, T], SVD called with the field name as str
+    import synth
+    from sparsespatialsampling_b200 import (SparseSpatialSampling, ExportData, Dataloader, write_svd_s_cube_to_file)
+    from sparsespatialsampling_b200.geometry import CubeGeometry, GeometryCoordinates2D
+    n_t = 12
+    xz = synth.airfoil2d_cloud(6000, seed=51)
+    th = np.linspace(0.0, 2.0 * np.pi, 41)
+    front = np.stack([0.5 + 0.5 * np.cos(th), 0.05 * np.sin(th)], 1)              # thin ellipse, closed ring
+    rear = np.stack([2.0 + 0.25 * np.cos(th), -0.3 + 0.04 * np.sin(th)], 1)
+    outside = lambda ring, c, a, b: ((xz[:, 0] - c[0]) / a) ** 2 + ((xz[:, 1] - c[1]) / b) ** 2 > 1.02
+    xz = xz[outside(front, (0.5, 0.0), 0.5, 0.05) & outside(rear, (2.0, -0.3), 0.25, 0.04)]
+    field = synth.wake_field(xz, 0, n_t, n_t, components=1, xc=1.0, yc=0.0)[:, 0]  # [N, T]
+    metric = field.std(dim=1).to(pt.float64)
+    bounds = [[pt.min(xz[:, 0]).item(), pt.min(xz[:, 1]).item()], [pt.max(xz[:, 0]).item(), pt.max(xz[:, 1]).item()]]
+    geometry = [CubeGeometry("domain", True, bounds[0], bounds[1]),
+                GeometryCoordinates2D("OAT15", False, front, refine=True),
+                GeometryCoordinates2D("NACA", False, rear, refine=True)]
+    times = pt.arange(n_t, dtype=pt.float64) * 0.5
+    s_cube = SparseSpatialSampling(xz, metric, geometry, str(tmp_path), "OAT15_small_area_variance_0.50", "OAT15",
+                                   uniform_levels=4, min_metric=0.5, n_jobs=8, max_delta_level=False)
+    s_cube.execute_grid_generation()
+    nc = s_cube.centers.size(0)
+    tree = orc.OracleTree(xz.numpy(), metric.numpy(), geometry, uniform_level=4, min_metric=0.5, sdm_order=1).refine()
+    assert np.array_equal(tree.all_centers, s_cube.centers.numpy())
+    assert np.array_equal(tree.all_levels, s_cube.levels.numpy())
+    # no cell of the grid lies completely inside a body
+    for ring, c, a, b in ((front, (0.5, 0.0), 0.5, 0.05), (rear, (2.0, -0.3), 0.25, 0.04)):
+        cc = s_cube.centers.numpy()
+        half = 0.5 * s_cube.size_initial_cell / 2.0 ** s_cube.levels.numpy().reshape(-1)
+        inside_all = np.ones(nc, dtype=bool)
+        for sx, sy in ((-1, -1), (-1, 1), (1, 1), (1, -1)):
+            px, py = cc[:, 0] + sx * half, cc[:, 1] + sy * half
+            inside_all &= ((px - c[0]) / a) ** 2 + ((py - c[1]) / b) ** 2 < 0.95
+        assert not inside_all.any()
+
+    export = ExportData(s_cube, write_times=times.tolist())
+    export.export(xz, field.unsqueeze(1), "p")
+    loader = Dataloader(str(tmp_path), "OAT15_small_area_variance_0.50.h5")
+    assert [float(t) for t in loader.write_times] == times.tolist()
+    p_s = loader.load_snapshot("p")
+    d, idx = orc.knn_search(xz.numpy(), s_cube.centers.numpy(), 8)
+    ref_p = orc.interpolate(orc.export_weights(d), idx, field.unsqueeze(1).numpy())[:, 0]
+    assert tuple(p_s.shape) == (nc, n_t)
+    assert np.abs(p_s.numpy() - ref_p).max() <= 1e-5 * np.abs(field.numpy()).max()
+    write_svd_s_cube_to_file("p", str(tmp_path), "OAT15_small_area_variance_0.50", export.new_file, 50, rank=int(1e5))
+    out = Dataloader(str(tmp_path), "OAT15_small_area_variance_0.50_p_svd.h5")._store()
+    s = np.asarray(out.read("constant/s")).reshape(-1)
+    s_ref, _, _ = orc.compute_svd(ref_p.astype(np.float32), loader.weights.numpy(), n_t)
+    assert s.shape[0] == n_t and np.abs(s[:4] - s_ref[:4]).max() <= 1e-4 * s_ref[0]
+    assert len([k for k in out.keys("constant") if k.startswith("mode_")]) == n_t       # 50 asked, 12 available
