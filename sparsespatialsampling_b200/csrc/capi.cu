@@ -92,8 +92,15 @@ int s3_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_p
     S3_REQUIRE(width >= 0 && height >= 0 && dst_pitch >= width && src_pitch >= width, "s3_copy2d_async: bad geometry");
     S3_REQUIRE(kind == 0 || kind == 1, "s3_copy2d_async: kind must be 0 (host to device) or 1 (device to host)");
     if (width == 0 || height == 0) return S3_OK;
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (width == dst_pitch && width == src_pitch) {
+        // dense on both sides: one linear copy (a 2-D host-to-device copy whose width equals the pitch measured
+        // 31.5 GB/s instead of 55, scripts/pitch_probe.py)
+        S3_CUDA(cudaMemcpyAsync(dst, src, (size_t)width * (size_t)height, k, (cudaStream_t)stream));
+        return S3_OK;
+    }
     S3_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)height,
-                              kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+                              k, (cudaStream_t)stream));
     return S3_OK;
 }
 
