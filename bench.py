@@ -381,6 +381,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (interp_gather_kernel; the step is two launches of it)
     b_algo = algorithmic_bytes(n_unique, n_cells, k, 1, N_SNAP) + algorithmic_bytes(n_unique, n_cells, k, 2, N_SNAP)
     achieved = b_algo / (ms_step * 1e-3) / 1e9
+    naive_bytes = sum(n_cells * k * comps * N_SNAP * 4 + n_cells * comps * N_SNAP * 4 + n_cells * k * 8 for comps in (1, 2))
     peak, peak_src = measured_peak()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -422,7 +423,10 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": {"staged": "interp_staged_kernel", "pipe": "interp_pipe_kernel",
                                 "direct": "interp_warpcell_kernel", "grouped": "interp_group_kernel"}[args.kernel],
-                     "algorithmic_bytes_per_step": b_algo, "frac_of_nominal_8TBs": achieved / 8000.0},
+                     "algorithmic_bytes_per_step": b_algo, "frac_of_nominal_8TBs": achieved / 8000.0,
+                     # what a gather without any cache re-use would move (every reference read from DRAM)
+                     "naive_gather_bytes_per_step": naive_bytes,
+                     "naive_gather_gbs": naive_bytes / (ms_step * 1e-3) / 1e9},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms.item(), "api": "ExportData.export(pinned host tensors) -> pinned host result; time windows pipelined over "
