@@ -107,3 +107,24 @@ def test_export_accepts_two_dimensional_scalar_field(cuda, tmp_path):
     exp2 = ExportData(g, write_files=False)
     with pytest.raises(ValueError):
         exp2.export(x, data.cuda(), "p")           # no write_times
+
+
+@pytest.mark.parametrize("m,t,d", [(1, 1, 0), (5, 1, 0), (5, 3, 0), (1, 7, 0), (40, 2, 2), (300, 5, 3), (2, 300, 0),
+                                   (1000, 17, 0)])
+@pytest.mark.parametrize("method", ["tc3", "tc", "simt"])
+def test_svd_degenerate_shapes(cuda, m, t, d, method):
+    # one snapshot, one cell, fewer cells than snapshots, snapshot counts that are no multiple of the TMA / UMMA tiles
+    import numpy as np
+    from oracle import s3_oracle as orc
+    from sparsespatialsampling_b200 import compute_svd
+    rng = np.random.default_rng(m * 31 + t)
+    a = rng.standard_normal((m, t) if d == 0 else (m, d, t)).astype(np.float32)
+    vol = rng.random(m) + 0.5
+    s, u, v = compute_svd(pt.from_numpy(a).cuda(), pt.from_numpy(vol), rank=3, method=method)
+    r = s.numel()
+    assert r == min(3, t, m * max(d, 1))
+    s_ref, _, _ = orc.compute_svd(a, vol, r)
+    tol = (5e-3 if method == "tc" else 2e-4) * max(float(s_ref[0]), 1e-12)
+    assert np.allclose(s.cpu().numpy(), s_ref[:r], atol=tol)
+    assert tuple(u.shape) == ((m, r) if d == 0 else (m, d, r)) and tuple(v.shape) == (t, r)
+    assert bool(pt.isfinite(u).all() and pt.isfinite(v).all() and pt.isfinite(s).all())
