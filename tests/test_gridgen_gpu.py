@@ -214,3 +214,45 @@ def test_full_size_configs_match_the_reference_run(cuda, name):
     assert str(tree.face_ids.numpy().dtype) == str(ref["faces_dtype"])
     assert sha(tree.face_ids.numpy()) == str(ref["faces_sha"])
     assert tree.all_nodes.shape[0] == int(ref["n_vertices"]) and sha(tree.all_nodes.numpy()) == str(ref["vertices_sha"])
+
+
+def _edge_cases():
+    rng = np.random.default_rng(0)
+    x, m = rng.random((500, 2)), rng.random(500)
+    x3, m3 = rng.random((300, 3)), rng.random(300)
+    box2 = lambda g: [g.CubeGeometry("d", True, [0, 0], [1, 1])]
+    box3 = lambda g: [g.CubeGeometry("d", True, [0, 0, 0], [1, 1, 1])]
+    return {
+        "plain_2d": (x, m, box2, dict(uniform_level=3, min_metric=0.7)),
+        "uniform_level_1": (x, m, box2, dict(uniform_level=1, min_metric=0.5)),
+        "n_cells_below_uniform_grid": (x, m, box2, dict(uniform_level=4, n_cells=50)),
+        "cells_per_iter_above_leaf_count": (x, m, box2, dict(uniform_level=2, min_metric=0.6, n_cells_iter_start=10000)),
+        "constant_metric": (x, np.ones(500), box2, dict(uniform_level=3, min_metric=0.9)),
+        "12_points": (x[:12], m[:12], box2, dict(uniform_level=2, min_metric=0.5)),
+        "as_many_points_as_neighbours": (x[:8], m[:8], box2, dict(uniform_level=2, min_metric=0.5)),
+        "plain_3d": (x3, m3, box3, dict(uniform_level=2, min_metric=0.6)),
+        "30_points_3d": (x3[:30], m3[:30], box3, dict(uniform_level=2, min_metric=0.5)),
+        "metric_reached_after_uniform": (x, m, box2, dict(uniform_level=5, min_metric=0.05)),
+        "body_covers_most_of_the_domain": (x, m, lambda g: [g.CubeGeometry("d", True, [0, 0], [1, 1]),
+                                                           g.CubeGeometry("b", False, [0.1, 0.1], [0.9, 0.9])],
+                                           dict(uniform_level=3, min_metric=0.5)),
+        "two_domains_last_is_root": (x, m, lambda g: [g.CubeGeometry("d1", True, [0, 0], [1, 1]),
+                                                     g.CubeGeometry("d2", True, [0.0, 0.0], [0.5, 0.5])],
+                                     dict(uniform_level=3, min_metric=0.5)),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_edge_cases()))
+def test_edge_configurations_match_oracle(cuda, name):
+    # corner cases of the control flow (tiny clouds, degenerate schedules, stopping right after the uniform phase, the
+    # root-cell rule with several domains): same leaves, levels and iteration log as the restatement of the reference
+    import sparsespatialsampling_b200.geometry as geo
+    from sparsespatialsampling_b200.s_cube import SamplingTree
+    from oracle import s3_oracle as orc
+    x, m, geoms, kw = _edge_cases()[name]
+    tree = SamplingTree(pt.from_numpy(x), pt.from_numpy(m), geoms(geo), sdm_order=1, **kw)
+    tree.refine()
+    ref = orc.OracleTree(x, m, geoms(geo), sdm_order=1, **kw).refine()
+    assert np.array_equal(tree.all_centers.numpy(), ref.all_centers)
+    assert np.array_equal(tree.all_levels.numpy(), ref.all_levels)
+    assert tree.data_final_mesh["cells_per_iter"] == ref.n_cells_log
