@@ -453,9 +453,13 @@ class ExportData:
             self._datawriter.write_data("metric", group=CONST, data=self._metric)
             self._datawriter.write_data("size_initial_cell", group=CONST, data=self._size_initial_cell)
             self._initialized_hdf5 = True
-            self._levels = None
-            self._metric = None
-            self._size_initial_cell = None
+            if not self._new_file:
+                # one file for all fields: the grid constants are written once and can go. With one file per field the
+                # reference drops them here as well (export.py:259-261) and then fails on the second field
+                # (create_dataset(data=None)); they are kept so that every per-field file is complete.
+                self._levels = None
+                self._metric = None
+                self._size_initial_cell = None
         else:
             if not self._new_file and self._datawriter is None:
                 self._datawriter = Datawriter(self._save_dir, f"{self._save_name}.h5", mode="a")

@@ -177,3 +177,45 @@ def test_oat15_example_flow_polygon_bodies(cuda, tmp_path):
     s_ref, _, _ = orc.compute_svd(ref_p.astype(np.float32), loader.weights.numpy(), n_t)
     assert s.shape[0] == n_t and np.abs(s[:4] - s_ref[:4]).max() <= 1e-4 * s_ref[0]
     assert len([k for k in out.keys("constant") if k.startswith("mode_")]) == n_t       # 50 asked, 12 available
+
+
+def test_export_options(cuda, tmp_path):
+    # ExportData options of the reference (export.py:41-126): one file per field, a neighbour count of the caller's
+    # choice, and appending a field to an existing file with a second ExportData object
+    import synth
+    from sparsespatialsampling_b200 import SparseSpatialSampling, ExportData, Dataloader
+    from sparsespatialsampling_b200.geometry import CubeGeometry, SphereGeometry
+    n_t = 5
+    coord = synth.cylinder2d_cloud(3000, seed=61)
+    p = synth.wake_field(coord, 0, n_t, n_t, components=1)
+    u = synth.wake_field(coord, 0, n_t, n_t, components=2)
+    times = [str(i) for i in range(n_t)]
+    geoms = [CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"]),
+             SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"])]
+    s_cube = SparseSpatialSampling(coord, synth.wake_metric(coord), geoms, str(tmp_path), "opt", "grid",
+                                   uniform_levels=4, min_metric=0.5)
+    s_cube.execute_grid_generation()
+    nc = s_cube.centers.size(0)
+
+    def reference(field, k):
+        d, idx = orc.knn_search(coord.numpy(), s_cube.centers.numpy(), k)
+        return orc.interpolate(orc.export_weights(d), idx, field.numpy())
+
+    # one file per field, 5 neighbours
+    export = ExportData(s_cube, write_new_file_for_each_field=True, n_neighbors=5, write_times=times)
+    assert export.new_file is True
+    export.export(coord, p, "p")
+    export.export(coord, u, "U")
+    for name, field in (("p", p), ("U", u)):
+        assert os.path.exists(tmp_path / f"opt_{name}.xdmf")
+        got = Dataloader(str(tmp_path), f"opt_{name}.h5").load_snapshot(name).numpy().reshape(nc, -1, n_t)
+        assert np.abs(got - reference(field, 5)).max() <= 1e-5 * float(field.abs().max())
+    # default file, then a second object appends another field to it
+    export = ExportData(s_cube, write_times=times)
+    export.export(coord, p, "p")
+    again = ExportData(s_cube, write_times=times, append_existing=True)
+    again.export(coord, u, "U")
+    loader = Dataloader(str(tmp_path), "opt.h5")
+    assert sorted(loader.field_names[times[0]]) == ["U", "p"]
+    assert np.abs(loader.load_snapshot("U").numpy() - reference(u, 8)).max() <= 1e-5 * float(u.abs().max())
+    assert np.abs(loader.load_snapshot("p").numpy() - reference(p, 8)[:, 0]).max() <= 1e-5 * float(p.abs().max())
