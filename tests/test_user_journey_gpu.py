@@ -219,3 +219,33 @@ def test_export_options(cuda, tmp_path):
     assert sorted(loader.field_names[times[0]]) == ["U", "p"]
     assert np.abs(loader.load_snapshot("U").numpy() - reference(u, 8)).max() <= 1e-5 * float(u.abs().max())
     assert np.abs(loader.load_snapshot("p").numpy() - reference(p, 8)[:, 0]).max() <= 1e-5 * float(p.abs().max())
+
+
+def test_svd_from_per_field_files_and_facade_options(cuda, tmp_path):
+    # write_svd_s_cube_to_file(new_file=True) reads <name>_<field>.h5 (utils.py:381-386); the facade hands the stopping
+    # and scheduling options through to the tree (sparse_spatial_sampling.py:86-115)
+    import synth
+    from sparsespatialsampling_b200 import (SparseSpatialSampling, ExportData, Dataloader, write_svd_s_cube_to_file)
+    from sparsespatialsampling_b200.geometry import CubeGeometry, SphereGeometry
+    n_t = 8
+    coord = synth.cylinder2d_cloud(3000, seed=71)
+    p = synth.wake_field(coord, 0, n_t, n_t, components=1)
+    times = [str(i) for i in range(n_t)]
+    geoms = [CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"]),
+             SphereGeometry("cylinder", False, synth.CYL2D["pos"], synth.CYL2D["radius"])]
+    metric = synth.wake_metric(coord)
+    kw = dict(uniform_levels=3, n_cells_max=400, max_delta_level=True, n_cells_iter_start=25, n_cells_iter_end=5)
+    s_cube = SparseSpatialSampling(coord, metric, geoms, str(tmp_path), "f", "grid", **kw)
+    s_cube.execute_grid_generation()
+    from oracle.topology_oracle import OracleTopology
+    ref = orc.OracleTree(coord.numpy(), metric.numpy(), geoms, uniform_level=3, n_cells=400, max_delta_level=True,
+                         n_cells_iter_start=25, n_cells_iter_end=5, sdm_order=1, topology=OracleTopology).refine()
+    assert np.array_equal(ref.all_centers, s_cube.centers.numpy())
+    assert np.array_equal(ref.face_ids, s_cube.faces.numpy()) and np.array_equal(ref.all_nodes, s_cube.vertices.numpy())
+
+    export = ExportData(s_cube, write_new_file_for_each_field=True, write_times=times)
+    export.export(coord, p, "p")
+    write_svd_s_cube_to_file(["p"], str(tmp_path), "f", export.new_file, 2, rank=3)
+    out = Dataloader(str(tmp_path), "f_p_svd.h5")._store()
+    assert np.asarray(out.read("constant/s")).reshape(-1).shape[0] == 3
+    assert sorted(k for k in out.keys("constant") if k.startswith("mode_")) == ["mode_1", "mode_2"]
