@@ -249,3 +249,29 @@ def test_svd_from_per_field_files_and_facade_options(cuda, tmp_path):
     out = Dataloader(str(tmp_path), "f_p_svd.h5")._store()
     assert np.asarray(out.read("constant/s")).reshape(-1).shape[0] == 3
     assert sorted(k for k in out.keys("constant") if k.startswith("mode_")) == ["mode_1", "mode_2"]
+
+
+def test_export_input_conventions_and_errors(cuda, tmp_path):
+    # export.py:154-200: no write times -> ValueError; a 1-D field -> ValueError; a [N, T] field is taken as a scalar
+    # field; CUDA tensors (rejected by the reference) are accepted here and give the same result as host tensors
+    import synth
+    from sparsespatialsampling_b200 import SparseSpatialSampling, ExportData
+    from sparsespatialsampling_b200.geometry import CubeGeometry
+    coord = synth.cylinder2d_cloud(2000, seed=81)
+    p = synth.wake_field(coord, 0, 4, 4, components=1)
+    s_cube = SparseSpatialSampling(coord, synth.wake_metric(coord),
+                                   [CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"])],
+                                   str(tmp_path), "e", "grid", uniform_levels=3, min_metric=0.4)
+    s_cube.execute_grid_generation()
+    export = ExportData(s_cube, write_files=False)
+    with pytest.raises(ValueError):
+        export.export(coord, p, "p")                                       # write_times never set
+    export.write_times = [str(i) for i in range(4)]
+    with pytest.raises(ValueError):
+        export.export(coord, p[:, 0, 0], "p")                              # 1-D field
+    export.export(coord, p[:, 0, :], "p")                                  # [N, T] -> [N, 1, T]
+    host = export.interpolated_fields.centers
+    assert tuple(host.shape) == (s_cube.centers.size(0), 1, 4)
+    export.export(coord.cuda(), p.cuda(), "p")
+    dev = export.interpolated_fields.centers
+    assert dev.is_cuda and pt.equal(dev.cpu(), host.cpu())
