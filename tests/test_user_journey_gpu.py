@@ -275,3 +275,29 @@ def test_export_input_conventions_and_errors(cuda, tmp_path):
     export.export(coord.cuda(), p.cuda(), "p")
     dev = export.interpolated_fields.centers
     assert dev.is_cuda and pt.equal(dev.cpu(), host.cpu())
+
+
+def test_export_from_a_reloaded_s_cube_object(cuda, tmp_path):
+    # examples/s3_for_cylinder3D_Re3900.py:117-122: the pickled s_cube_<name>.pt is loaded again, pointed at a new
+    # directory and exported from
+    import synth
+    from sparsespatialsampling_b200 import SparseSpatialSampling, ExportData, Dataloader
+    from sparsespatialsampling_b200.geometry import CubeGeometry
+    coord = synth.cylinder2d_cloud(2000, seed=91)
+    p = synth.wake_field(coord, 0, 3, 3, components=1)
+    first = tmp_path / "first"
+    s_cube = SparseSpatialSampling(coord, synth.wake_metric(coord),
+                                   [CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"])],
+                                   str(first), "r", "grid", uniform_levels=3, min_metric=0.4)
+    s_cube.execute_grid_generation()
+    direct = ExportData(s_cube, write_times=["0", "1", "2"], write_files=False)
+    direct.export(coord, p, "p")
+    expected = direct.interpolated_fields.centers.cpu().clone()
+
+    loaded = pt.load(os.path.join(first, "s_cube_r.pt"), weights_only=False)
+    second = tmp_path / "second"
+    loaded.save_path = str(second)
+    export = ExportData(loaded, write_times=["0", "1", "2"])
+    export.export(coord, p, "p")
+    got = Dataloader(str(second), "r.h5").load_snapshot("p")
+    assert pt.equal(got, expected[:, 0])
