@@ -15,12 +15,12 @@ from .knn import KnnIndex
 from .export import ExportData, Fields
 from .data import Datawriter, Dataloader, XDMFWriter
 from .svd import compute_svd, compute_svd_sharded
-from .utils import write_svd_s_cube_to_file
+from .utils import write_svd_s_cube_to_file, export_fields_batchwise, export_openfoam_fields
 from . import geometry
 
 _logging.getLogger(__name__).addHandler(_logging.NullHandler())
 
 __version__ = "0.1.0"
 __all__ = ["SparseSpatialSampling", "SamplingTree", "list_geometries", "interpolate_data", "interp_gather", "KnnIndex",
-           "ExportData", "Fields", "Datawriter", "Dataloader", "XDMFWriter", "compute_svd", "compute_svd_sharded", "write_svd_s_cube_to_file",
+           "ExportData", "Fields", "Datawriter", "Dataloader", "XDMFWriter", "compute_svd", "compute_svd_sharded", "write_svd_s_cube_to_file", "export_fields_batchwise", "export_openfoam_fields",
            "geometry"]

@@ -301,3 +301,42 @@ def test_export_from_a_reloaded_s_cube_object(cuda, tmp_path):
     export.export(coord, p, "p")
     got = Dataloader(str(second), "r.h5").load_snapshot("p")
     assert pt.equal(got, expected[:, 0])
+
+
+def test_batchwise_export_loop(cuda, tmp_path):
+    # the loop of export_openfoam_fields (utils.py:204-226) with a synthetic reader: ragged last batch, a field that
+    # does not exist (reader returns None) is skipped, the file equals a one-shot export
+    import synth
+    from sparsespatialsampling_b200 import (SparseSpatialSampling, ExportData, Dataloader, export_fields_batchwise,
+                                            export_openfoam_fields)
+    from sparsespatialsampling_b200.geometry import CubeGeometry
+    n_t = 7
+    coord = synth.cylinder2d_cloud(2000, seed=101)
+    fields = {"p": synth.wake_field(coord, 0, n_t, n_t, components=1), "U": synth.wake_field(coord, 0, n_t, n_t, components=2)}
+    times = [str(i) for i in range(n_t)]
+    s_cube = SparseSpatialSampling(coord, synth.wake_metric(coord),
+                                   [CubeGeometry("domain", True, synth.CYL2D["lower"], synth.CYL2D["upper"])],
+                                   str(tmp_path), "b", "grid", uniform_levels=3, min_metric=0.4)
+    s_cube.execute_grid_generation()
+    calls = []
+
+    def reader(name, batch_times):
+        calls.append((name, list(batch_times)))
+        if name not in fields:
+            return None, None
+        cols = [times.index(t) for t in batch_times]
+        return coord, fields[name][:, :, cols]
+
+    export = ExportData(s_cube, write_times=times)
+    export_fields_batchwise(export, reader, ["p", "missing", "U"], batch_size=3)
+    assert [c[1] for c in calls if c[0] == "p"] == [["0", "1", "2"], ["3", "4", "5"], ["6"]]
+    loader = Dataloader(str(tmp_path), "b.h5")
+    assert sorted(loader.field_names[times[0]]) == ["U", "p"]
+    once = ExportData(s_cube, write_times=times, write_files=False)
+    for name in ("p", "U"):
+        once.export(coord, fields[name], name)
+        expected = once.interpolated_fields.centers.cpu()
+        got = loader.load_snapshot(name).reshape(expected.shape)
+        assert pt.equal(got, expected), name
+    with pytest.raises(ImportError):                                       # flowtorch is not part of this image
+        export_openfoam_fields(export, str(tmp_path), [[0, 0], [1, 1]])
