@@ -36,16 +36,6 @@ int s3_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t s3_launch_count(void);
 
-/* tuning knobs (benchmarking): key 0 = cells per CTA of the direct interpolation kernel, ...,
- * key 10 = 16-row K-blocks accumulated in TMEM per segment of the tensor-core Gram kernel (default 8),
- * key 11 = segments summed in fp32 registers per fp64 flush (default 128), key 13 = how a warp of the interpolation
- * kernel broadcasts a cell's (index, weight) pairs: -1 by k (default), 0 SHFL, 1 REDUX, 2 / 3 shared memory,
- * 4 byte-offset table, 52 / 53 / 54 / 58 the same with fenced batches of 2 / 3 / 4 / 8 row loads; keys 15-18 = grouped kernel: warps per CTA, distinct rows in flight per lane (1, 2, 3, 4, 6,
- * 8), CTAs per SM the register allocation must allow (2..6), column vectors per lane (1, 2),
- * key 14 = Gram kernel in clusters of two CTAs that share the B operand by TMA multicast (default 1),
- * key 20 = shared-memory carve-out (percent) requested for the warp-per-cell kernel, -1 = driver default */
-int s3_set_tuning(int key, int value);
-
 /* ---- k-nearest-neighbour index over the original point cloud ---------------------------------
  * replaces sklearn KNeighborsRegressor / NearestNeighbors as used in
  *   sparseSpatialSampling/s_cube.py:161-163 (fit), :224, :328, :372 (predict)
@@ -167,57 +157,25 @@ int s3_sumsq(const double* d_x, int64_t n, double* d_out, void* stream);
 
 /* ---- export-stage interpolation ---------------------------------------------------------------
  * replaces interpolate_data (sparseSpatialSampling/export.py:446-468):
- *   out[c, :] = sum_j w[c, j] * data[idx[c, j], :],  data [n_src, row_len], out [n_cells, row_len]
+ *   out[c, d, t] = sum_j w[c, j] * data[idx[c, j], d, t]
+ * data is the reference's [n_src, n_comp, n_cols] snapshot batch (t contiguous) with explicit strides in
+ * ELEMENTS: row_stride between source points, comp_stride between the components of a point; the result
+ * [n_cells, n_comp, n_cols] likewise (out_row_stride, out_comp_stride). Dense tensors: comp_stride = n_cols,
+ * row_stride = n_comp * n_cols. The kernel is built for row pitches that are multiples of 128 bytes (every warp
+ * request then covers whole cache lines); any stride is accepted, 16-byte aligned strides and base
+ * pointers take the 128-bit path, everything else a scalar one.
  * dtypes: (data F32, out F32): w is fp32, fp32 FMA accumulation;
  *         (data F32|F64, out F64): w is fp64, products and sequential adds in fp64 (reference order).
  * d_out_row: optional int32 [n_cells] -- row of `out` that receives cell c (cells may be passed in
- * any processing order, e.g. Morton order); NULL = identity.                                       */
+ * any processing order, e.g. Morton order); NULL = identity. 1 <= k <= 64.                           */
+int s3_interp_gather_strided(const void* d_data, int data_dtype, int64_t n_src, int n_comp, int64_t n_cols,
+                             int64_t row_stride, int64_t comp_stride, const int32_t* d_idx, const void* d_w,
+                             int64_t n_cells, int k, const int32_t* d_out_row, void* d_out, int out_dtype,
+                             int64_t out_row_stride, int64_t out_comp_stride, void* stream);
+/* dense special case: data [n_src, row_len], out [n_cells, row_len] */
 int s3_interp_gather(const void* d_data, int data_dtype, int64_t n_src, int64_t row_len,
                      const int32_t* d_idx, const void* d_w, int64_t n_cells, int k,
                      const int32_t* d_out_row, void* d_out, int out_dtype, void* stream);
-
-/* Grouped fp32 variant of the same operator (experimental): a warp interpolates
- * s3_interp_group_size() = 4 consecutive cells (processing order) and loads every DISTINCT source row of
- * the group once, folding it into up to 4 accumulators.
- * s3_interp_groups_build (once per KNN cache): from d_idx int32 / d_w fp32 [n_cells, k] builds, per group g
- *   (n_groups = ceil(n_cells / 4)): d_cnt int32 [n_groups] number of distinct rows, d_ent int32
- *   [n_groups, 4*k, 2] = {row, membership mask} in order of first appearance, d_wts fp32 [n_groups, 4*k, 4]
- *   weight of the row for each cell of the group (0 = not referenced).
- * s3_interp_grouped: same result as s3_interp_gather(F32, F32) up to the fp32 summation order (terms of a
- *   cell are added in the order of the group's list). Requires row_len % 4 == 0 and 16-byte aligned
- *   buffers. A row a cell does not reference is skipped by predicate, never multiplied by zero.       */
-int s3_interp_group_size(void);
-int s3_interp_groups_build(const int32_t* d_idx, const float* d_w, int64_t n_cells, int k, int32_t* d_cnt,
-                           void* d_ent, void* d_wts, void* stream);
-int s3_interp_grouped(const void* d_data, int64_t n_src, int64_t row_len, const int32_t* d_cnt,
-                      const void* d_ent, const void* d_wts, int64_t n_cells, int k,
-                      const int32_t* d_out_row, void* d_out, int out_dtype, void* stream);
-
-/* Staged fp32 variant of the same operator: cells are grouped in tiles of 32 (processing order); the
- * unique source rows of a tile are copied once into shared memory by TMA bulk copies and re-used by
- * all cells of the tile.
- * s3_interp_tiles_build (once per KNN cache): from d_idx int32 [n_cells, k] (processing order) builds
- *   d_tile_rows int32 [n_tiles, 32*k] (unique rows, ascending), d_tile_nrows int32 [n_tiles],
- *   d_tile_lidx uint16 [n_tiles, 32*k] (position of every reference in its tile's row list).
- * s3_interp_staged: d_w fp32 [n_tiles*32, k] (zero padded to full tiles); max_rows = largest entry of
- *   d_tile_nrows (sizes the staging buffer; larger tiles fall back to direct loads);
- *   chunk_cols = 128 | 256 columns staged per CTA. Requires row_len % 4 == 0.                        */
-int s3_interp_tiles_build(const int32_t* d_idx, int64_t n_cells, int k, int32_t* d_tile_rows,
-                          int32_t* d_tile_nrows, uint16_t* d_tile_lidx, void* stream);
-int s3_interp_staged(const float* d_data, int64_t n_src, int64_t row_len, const int32_t* d_tile_rows,
-                     const int32_t* d_tile_nrows, const uint16_t* d_tile_lidx, const float* d_w,
-                     int64_t n_cells, int k, int max_rows, int chunk_cols, const int32_t* d_out_row,
-                     float* d_out, void* stream);
-
-/* Pipelined persistent variant of s3_interp_staged (same tile structures): one CTA per SM, a producer warp
- * feeds a ring of shared-memory stages with TMA bulk copies while 8 consumer warps interpolate from the
- * previous stages. stage_rows = rows held per stage (0 = max_rows; further rows of a tile are read
- * directly); n_ctas = grid size (0 = number of SMs); use_gather4 != 0: fetch the rows four at a time with
- * the Blackwell TMA gather (cp.async.bulk.tensor.2d...tile::gather4) instead of one bulk copy per row.   */
-int s3_interp_pipelined(const float* d_data, int64_t n_src, int64_t row_len, const int32_t* d_tile_rows,
-                        const int32_t* d_tile_nrows, const uint16_t* d_tile_lidx, const float* d_w,
-                        int64_t n_cells, int k, int max_rows, int chunk_cols, int stage_rows, int n_ctas,
-                        int use_gather4, const int32_t* d_out_row, float* d_out, void* stream);
 
 /* ---- streaming ingest -----------------------------------------------------------------------------
  * the reference feeds snapshot batches from host memory (export.py:128-167, utils.py:155-226). A window of the

@@ -1,0 +1,99 @@
+"""
+A/B lab of the interpolation kernel on the bench workload (C2 tables): every launch variant x both layouts, one JSON
+line each. Run on the GPU box:  python scripts/interp_lab.py [--variants "2=2;3=1;..."] > gpurun_out/lab.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch as pt
+
+import bench
+import synth
+import sparsespatialsampling_b200 as s3
+from sparsespatialsampling_b200 import _lib
+from sparsespatialsampling_b200.export import KnnTables
+from sparsespatialsampling_b200.interpolate import alloc_snapshots
+from sparsespatialsampling_b200.knn import KnnIndex
+
+DEFAULTS = {1: 8, 2: 0, 3: -1, 4: 0, 5: -1, 6: 0, 7: 1}
+VARIANTS = ["", "3=1", "2=2", "2=2,3=1", "7=4", "7=4,3=1", "7=4,2=2", "6=1", "6=1,3=1", "6=1,7=4", "6=1,2=2",
+            "1=4", "1=16", "1=16,3=1", "4=256", "4=512", "4=256,3=1", "1=4,7=4", "5=0", "5=50"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variants", default="")
+    ap.add_argument("--snapshots", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--k26", action="store_true", help="3-D style tables (k = 26) on a synthetic 3-D cloud instead of C2")
+    args = ap.parse_args()
+    dev = pt.device("cuda", 0)
+    pt.cuda.set_device(dev)
+    T = args.snapshots
+    if args.k26:
+        x = synth.cylinder3d_cloud(1000000, seed=0)
+        xd = x.to(dev)
+        g = pt.Generator().manual_seed(1)
+        lo, hi = pt.tensor(synth.CYL3D["lower"]), pt.tensor(synth.CYL3D["upper"])
+        centers = (lo + pt.rand((200000, 3), generator=g, dtype=pt.float64) * (hi - lo)).to(dev)
+        k = 26
+    else:
+        x = synth.cylinder2d_cloud(bench.N_POINTS, seed=0)
+        xd = x.to(dev)
+        metric = synth.wake_metric(xd).cpu()
+        sc = s3.SparseSpatialSampling(x, metric, bench.geometries(s3.geometry), "/tmp/s3b200_lab", "c2",
+                                      uniform_levels=5, min_metric=0.75)
+        sc.execute_grid_generation()
+        centers = sc.centers.to(dev)
+        k = 8
+    tables = KnnTables(KnnIndex(xd), centers, k)
+    nc = tables.n
+    n_unique = int(pt.unique(tables.idx_sorted).numel())
+    fields = {}
+    for comps in (1, 2):
+        f = synth.wake_field(xd, 0, T, T, comps)
+        fp = alloc_snapshots(xd.size(0), comps, T, device=dev, zero=True)
+        fp.copy_(f)
+        fields[comps] = {"dense": (f, pt.empty((nc, comps, T), device=dev)),
+                         "pitched": (fp, alloc_snapshots(nc, comps, T, device=dev))}
+    b_algo = sum(bench.algorithmic_bytes(n_unique, nc, k, c, T) for c in (1, 2))
+    peak, _ = bench.measured_peak()
+    variants = [v for v in args.variants.split(";")] if args.variants else VARIANTS
+    base = {}
+    for var in variants:
+        for key, val in DEFAULTS.items():
+            _lib.tune(key, val)
+        for kv in [t for t in var.split(",") if t]:
+            key, val = kv.split("=")
+            _lib.tune(int(key), int(val))
+        for layout in ("pitched", "dense"):
+            def step():
+                for comps in (1, 2):
+                    d, o = fields[comps][layout]
+                    tables.interpolate(d, pt.float32, out=o)
+            for _ in range(3):
+                step()
+            pt.cuda.synchronize()
+            e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            pt.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            res = tuple(fields[c][layout][1].clone() for c in (1, 2))
+            if not base:
+                base["res"] = res
+            same = all(pt.equal(a, b) for a, b in zip(res, base["res"]))
+            print(json.dumps({"variant": var or "default", "layout": layout, "k": k, "T": T, "n_cells": nc,
+                              "ms_per_step": round(ms, 4), "frac": round(b_algo / (ms * 1e-3) / 1e9 / peak, 4),
+                              "bit_identical": same}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -74,7 +74,8 @@ def main():
     ap.add_argument("--n-cells-max", type=int, default=0)
     ap.add_argument("--sample", type=int, default=512)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--tune", default="", help="comma separated key=value pairs for s3_set_tuning, e.g. 5=1,8=0")
+    ap.add_argument("--tune", default="", help="comma separated key=value pairs for s3x_tune (csrc/interp.cu), e.g. 2=1,3=0")
+    ap.add_argument("--dense", action="store_true", help="the reference's dense [N, D, T] layout instead of 128-byte pitched rows")
     ap.add_argument("--lattice-vertices", action="store_true", help="exact_topology=False")
     ap.add_argument("--e2e", action="store_true", help="also time the host-to-host export (256 snapshots): DMA vs row gather")
     args = ap.parse_args()
@@ -84,7 +85,7 @@ def main():
         from sparsespatialsampling_b200 import _lib
         for kv in args.tune.split(","):
             key, val = kv.split("=")
-            _lib.check(_lib.load().s3_set_tuning(int(key), int(val)))
+            _lib.tune(int(key), int(val))
     x, geoms, wake, grid_kw = config(args.name, args.n_cells_max)
     d = x.size(1)
     k = 8 if d == 2 else 26
@@ -143,9 +144,14 @@ def main():
     w_ref = orc.export_weights(d_ref)
     np.testing.assert_allclose(tables.w64[pt.from_numpy(sample).to(dev)].cpu().numpy(), w_ref, rtol=1e-13)
 
-    data = pt.empty((x.size(0), 1, T), dtype=pt.float32, device=dev)
+    from sparsespatialsampling_b200.interpolate import alloc_snapshots
+    if args.dense:
+        data = pt.empty((x.size(0), 1, T), dtype=pt.float32, device=dev)
+        out = pt.empty((nc, 1, T), dtype=pt.float32, device=dev)
+    else:
+        data = alloc_snapshots(x.size(0), 1, T, device=dev)
+        out = alloc_snapshots(nc, 1, T, device=dev)
     fill_field(data, xd, T, 1, wake["xc"], wake["yc"])
-    out = pt.empty((nc, 1, T), dtype=pt.float32, device=dev)
     tables.interpolate(data, pt.float32, out=out)
     pt.cuda.synchronize()
     e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
@@ -247,7 +253,7 @@ def main():
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
     print(json.dumps({
-        "config": args.name, "n_points": int(x.size(0)), "dim": d, "k": k, "snapshots": T, "n_cells": int(nc),
+        "config": args.name, "layout": "dense" if args.dense else "pitched", "tune": args.tune or None, "n_points": int(x.size(0)), "dim": d, "k": k, "snapshots": T, "n_cells": int(nc),
         "grid_gen_s": info["t_total"], "t_uniform": info["t_uniform"], "t_adaptive": info["t_adaptive"],
         "t_geometry": info["t_geometry"], "t_renumbering": info["t_renumbering"], "t_knn_build_gridgen": info["t_knn_build"],
         "setup_s": t_setup, "iterations": info["iterations"], "levels": [info["min_level"], info["max_level"]],

@@ -30,7 +30,6 @@ _SIGNATURES = {
     "s3_last_error": (c_char_p, []),
     "s3_version": (c_int, []),
     "s3_launch_count": (c_int64, []),
-    "s3_set_tuning": (c_int, [c_int, c_int]),
     "s3_knn_build": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
     "s3_knn_free": (c_int, [c_void_p]),
     "s3_knn_query": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -65,15 +64,8 @@ _SIGNATURES = {
     "s3_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "s3_interp_gather": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                  c_void_p, c_int, c_void_p]),
-    "s3_interp_group_size": (c_int, []),
-    "s3_interp_groups_build": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "s3_interp_grouped": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
-                                  c_void_p, c_int, c_void_p]),
-    "s3_interp_tiles_build": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "s3_interp_staged": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-                                 c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "s3_interp_pipelined": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "s3_interp_gather_strided": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                         c_int64, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "s3_copy2d_async": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "s3_gather_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "s3_svd_row_means": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
@@ -102,10 +94,11 @@ def load():
             fn.restype = res
             fn.argtypes = args
         _lib = lib
-        # S3B200_TUNE="key=value,...": kernel tuning knobs (s3_set_tuning) applied at load, for A/B runs of the tests
+        # A/B harness hook of the kernels (s3x_tune, not part of include/s3b200.h): S3B200_TUNE="key=value,..."
+        lib.s3x_tune.restype, lib.s3x_tune.argtypes = c_int, [c_int, c_int]
         for kv in [t for t in os.environ.get("S3B200_TUNE", "").split(",") if t]:
             key, value = kv.split("=")
-            check(lib.s3_set_tuning(int(key), int(value)))
+            check(lib.s3x_tune(int(key), int(value)))
     return _lib
 
 
@@ -120,16 +113,21 @@ def require_cuda():
         raise S3Error("s3b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
 
 
-def ptr(t):
-    """Device pointer of a (contiguous) tensor, or NULL for None."""
+def ptr(t, strided: bool = False):
+    """Device pointer of a (contiguous) tensor, or NULL for None; ``strided``: the call passes the strides itself."""
     if t is None:
         return None
-    assert t.is_contiguous(), "tensor passed to the C-ABI must be contiguous"
+    assert strided or t.is_contiguous(), "tensor passed to the C-ABI must be contiguous"
     return c_void_p(t.data_ptr())
 
 
 def stream_ptr():
     return c_void_p(pt.cuda.current_stream().cuda_stream)
+
+
+def tune(key: int, value: int) -> None:
+    """A/B harness hook (scripts/interp_lab.py): kernel launch knobs, see csrc/interp.cu."""
+    check(load().s3x_tune(int(key), int(value)))
 
 
 def launch_count() -> int:

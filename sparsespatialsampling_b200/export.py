@@ -25,7 +25,7 @@ import torch as pt
 from . import _lib
 from .const import GRID, CONST, FACES, CENTERS, VERTICES, DATA
 from .data import Datawriter
-from .interpolate import interp_gather, StagedTiles, GroupTables
+from .interpolate import interp_gather, pitched_columns
 from .knn import KnnIndex, default_n_neighbors
 
 logger = logging.getLogger(__name__)
@@ -58,46 +58,11 @@ class KnnTables:
         self.out_row = perm.contiguous()
         self.n = q.size(0)
         self.k = k
-        self._tiles = None
-        self._groups = None
-        self._groups_compact = None
-        # "grouped" (a warp interpolates 4 consecutive cells and loads their distinct rows once), "direct" (warp per
-        # cell) or "staged" / "pipe" (TMA-staged tiles, experimental)
-        self.mode = self.default_mode
-        self.chunk_cols = 256
-        self.stage_rows = 0
-        self.n_ctas = 0
-        self.gather4 = True
-
-    # S3B200_INTERP_MODE selects the interpolation kernel of every KnnTables object (A/B runs): direct | grouped
-    default_mode = os.environ.get("S3B200_INTERP_MODE", "direct")
-
-    @property
-    def groups(self) -> GroupTables:
-        """Tables of the grouped kernel, built on first use."""
-        if self._groups is None:
-            self._groups = GroupTables(self.idx_sorted, self.w32_sorted)
-        return self._groups
-
-    @property
-    def tiles(self):
-        """Tile structures of the staged kernel, built on first use."""
-        if self._tiles is None and 32 * self.k <= 2048:
-            self._tiles = StagedTiles(self.idx_sorted, self.w32_sorted)
-        return self._tiles
+        self._inflight = []                  # (event, host tensors) of streamed batches still being copied
 
     def interpolate(self, data: pt.Tensor, out_dtype, out: pt.Tensor = None) -> pt.Tensor:
-        if out is None:
-            out = pt.empty((self.n,) + tuple(data.shape[1:]), dtype=out_dtype, device=data.device)
-        row_len = data.numel() // max(data.size(0), 1)
-        if (self.mode in ("staged", "pipe") and self.tiles is not None and out_dtype == pt.float32 and
-                data.dtype == pt.float32 and row_len % 4 == 0):
-            return self.tiles.interpolate(data, out=out, out_row=self.out_row, chunk_cols=self.chunk_cols,
-                                          pipelined=self.mode == "pipe", stage_rows=self.stage_rows,
-                                          n_ctas=self.n_ctas, gather4=self.gather4)
-        if (self.mode == "grouped" and out_dtype == pt.float32 and data.dtype == pt.float32 and row_len % 4 == 0 and
-                data.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0):
-            return self.groups.interpolate(data, out=out, out_row=self.out_row)
+        """``[N, D, T]`` / ``[N, T]`` device batch (any row pitch, T contiguous; a pitch that is a multiple of 128 bytes
+        is the fast layout, see ``interpolate.alloc_snapshots``) -> ``[Nc, D, T]`` in the reference's cell order."""
         w = self.w32_sorted if out_dtype == pt.float32 else self.w64_sorted
         return interp_gather(data, self.idx_sorted, w, out=out, out_row=self.out_row, out_dtype=out_dtype)
 
@@ -133,9 +98,10 @@ class KnnTables:
                 pt.cuda.synchronize(dev)
                 self._stream_buffers.clear()
             with pt.cuda.device(dev):
-                st = {"inp": [pt.empty((n_src, comps, chunk), dtype=pt.float32, device=dev) for _ in range(2)],
-                      "out": [pt.empty((self.n, comps, chunk), dtype=pt.float32, device=dev) for _ in range(2)],
-                      "done": None}
+                pitch = pitched_columns(chunk)              # 128-byte aligned rows whatever the window length
+                st = {"inp": [pt.empty((n_src, comps, pitch), dtype=pt.float32, device=dev) for _ in range(2)],
+                      "out": [pt.empty((self.n, comps, pitch), dtype=pt.float32, device=dev) for _ in range(2)],
+                      "done": None, "pitch": pitch}
             self._stream_buffers[key] = st
         return st
 
@@ -153,14 +119,14 @@ class KnnTables:
         """
         Host-to-host interpolation of a pinned fp32 snapshot batch ``[N, D, T]`` as a three-stage pipeline over windows
         of the time axis: host -> device transfer of window c+1 | interpolation kernel on window c | pitched D2H copy of
-        window c-1, each on its own stream (PCIe is full duplex). ``gather=True``: the transfer is a kernel that reads
-        the pinned batch over PCIe and fetches only the source rows the tables reference into a compact staging buffer
-        (``s3_gather_rows``; 48 GB/s on this pool whatever the fraction, less under full-duplex load);
-        ``gather=False``: one pitched DMA copy of the whole window (52-55 GB/s, all rows). Default: gather when the
-        tables reference less than 60 % of the source points (measured on the bench workload, 88 % referenced: DMA
-        29.8 ms per step, gather 35 ms). Returns the pinned host result ``[Nc, D, T]``; with
-        ``sync=False`` the call only enqueues the work (the next batch's transfers then overlap this batch's tail) and
-        the result is valid after ``wait_host()``.
+        window c-1, each on its own stream (PCIe is full duplex). The device staging buffers keep a row pitch that is a
+        multiple of 128 bytes whatever the window length (the layout the kernel is built for). ``gather=True``: the
+        transfer is a kernel that reads the pinned batch over PCIe and fetches only the source rows the tables
+        reference into a compact staging buffer (``s3_gather_rows``); ``gather=False``: one pitched DMA copy of the
+        whole window (all rows). Default: gather when the tables reference less than 60 % of the source points.
+        Returns the pinned host result ``[Nc, D, T]``; with ``sync=False`` the call only enqueues the work (the next
+        batch's transfers then overlap this batch's tail): the result is valid after ``wait_host()`` and ``data`` must
+        not be modified before ``wait_input()`` returned.
         """
         lib = _lib.load()
         assert data.device.type == "cpu" and data.dtype == pt.float32 and data.is_contiguous() and data.dim() == 3
@@ -169,7 +135,7 @@ class KnnTables:
         dev = self.idx_sorted.device
         n_src, comps, t = data.shape
         if out is None:
-            out = pt.empty((self.n, comps, t), dtype=pt.float32).pin_memory()
+            out = pt.empty((self.n, comps, t), dtype=pt.float32, pin_memory=True)
         assert out.is_pinned() and out.is_contiguous() and tuple(out.shape) == (self.n, comps, t)
         chunk = min(int(chunk_snapshots), t) if chunk_snapshots else self.default_window(n_src, comps, t)
         if gather is None:
@@ -181,15 +147,13 @@ class KnnTables:
         else:
             n_stage = n_src
         st = self._stream_state(dev, n_stage, comps, chunk)
+        pitch = st["pitch"]
         h2d, d2h = self._copy_streams
         compute = pt.cuda.current_stream(dev)
         n_chunks = (t + chunk - 1) // chunk
         ev_in = [pt.cuda.Event() for _ in range(n_chunks)]
         ev_k = [pt.cuda.Event() for _ in range(n_chunks)]
         ev_out = [pt.cuda.Event() for _ in range(n_chunks)]
-        keep = getattr(self, "_host_keepalive", [])
-        keep.append((data, out))                                # the copies are asynchronous: hold on to the host tensors
-        self._host_keepalive = keep[-8:]
         with pt.cuda.device(dev):
             ev_start = pt.cuda.Event()
             ev_start.record(compute)
@@ -201,67 +165,110 @@ class KnnTables:
                 t0 = c * chunk
                 tc = min(chunk, t - t0)
                 b = c & 1
-                full = tc == chunk
-                # a shorter last window uses a dense view of the same buffers
-                inp = st["inp"][b] if full else st["inp"][b].view(-1)[:n_stage * comps * tc].view(n_stage, comps, tc)
-                res = st["out"][b] if full else st["out"][b].view(-1)[:self.n * comps * tc].view(self.n, comps, tc)
+                inp = st["inp"][b][:, :, :tc]                   # shorter last window: same pitch, fewer columns
+                res = st["out"][b][:, :, :tc]
                 if c >= 2:
                     h2d.wait_event(ev_k[c - 2])               # the kernel that read this input buffer is done
                 if gather:
                     # half an SM-wave of CTAs is enough to saturate the PCIe reads and leaves room for the
                     # interpolation kernel of the previous window
                     _lib.check(lib.s3_gather_rows(data.data_ptr() + t0 * 4, t, _lib.ptr(rows_mat), rows_mat.numel(), tc,
-                                                  inp.data_ptr(), tc, 74, h2d.cuda_stream))
+                                                  inp.data_ptr(), pitch, 74, h2d.cuda_stream))
                 else:
-                    _lib.check(lib.s3_copy2d_async(inp.data_ptr(), tc * 4, data.data_ptr() + t0 * 4, t * 4, tc * 4,
+                    _lib.check(lib.s3_copy2d_async(inp.data_ptr(), pitch * 4, data.data_ptr() + t0 * 4, t * 4, tc * 4,
                                                    n_src * comps, 0, h2d.cuda_stream))
                 ev_in[c].record(h2d)
                 compute.wait_event(ev_in[c])
                 if c >= 2:
                     compute.wait_event(ev_out[c - 2])         # the copy that drained this output buffer is done
-                if gather and self.mode == "grouped" and tc % 4 == 0:
-                    if self._groups_compact is None:
-                        self._groups_compact = GroupTables(idx_compact, self.w32_sorted)
-                    self._groups_compact.interpolate(inp, out=res, out_row=self.out_row)
-                elif gather:
+                if gather:
                     interp_gather(inp, idx_compact, self.w32_sorted, out=res, out_row=self.out_row, out_dtype=pt.float32)
                 else:
                     self.interpolate(inp, pt.float32, out=res)
                 ev_k[c].record(compute)
                 d2h.wait_event(ev_k[c])
-                _lib.check(lib.s3_copy2d_async(out.data_ptr() + t0 * 4, t * 4, res.data_ptr(), tc * 4, tc * 4,
+                _lib.check(lib.s3_copy2d_async(out.data_ptr() + t0 * 4, t * 4, res.data_ptr(), pitch * 4, tc * 4,
                                                self.n * comps, 1, d2h.cuda_stream))
                 ev_out[c].record(d2h)
             st["done"] = ev_out[-1]
-            self._host_done = ev_out[-1]
+        # the copies are asynchronous: hold on to the host tensors until THEIR events completed (not by count)
+        self._inflight = [e for e in self._inflight if not e[0].query()]
+        self._inflight.append((ev_out[-1], ev_in[-1], data, out))
         if sync:
             self.wait_host()
         return out
 
+    def wait_input(self) -> None:
+        """Block until the host -> device reads of all batches issued so far are done (``data`` may be re-used)."""
+        for entry in self._inflight:
+            entry[1].synchronize()
+
     def wait_host(self) -> None:
         """Block until the results of all ``interpolate_host`` calls issued so far are in host memory."""
-        ev = getattr(self, "_host_done", None)
-        if ev is not None:
-            ev.synchronize()
-            self._host_done = None
-            self._host_keepalive = []
+        for entry in self._inflight:
+            entry[0].synchronize()
+        self._inflight = []
 
     def broadcast_(self, src: int = 0):
         """Share the tables of rank ``src`` with all ranks (NCCL over NVLink; one-off before the export loop)."""
         from .parallel import broadcast_tensors
         broadcast_tensors([self.idx_sorted, self.w32_sorted, self.w64_sorted, self.out_row, self.idx, self.w64], src)
-        self._tiles = None
-        self._groups = None
-        self._groups_compact = None
         self._rows_unique = None
         return self
+
+    @classmethod
+    def share(cls, tables: "KnnTables", device, src: int = 0, group=None) -> "KnnTables":
+        """
+        Sharded export: rank ``src`` passes the tables it built, every other rank passes ``None`` and
+        receives a copy -- one header + six tensor broadcasts (NCCL over NVLink; gloo moves them through the host).
+        This is the only collective of the export stage; the interpolation itself has none.
+        """
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return tables
+        dev = pt.device(device)
+        on_host = dist.get_backend(group) == "gloo"
+        root = dist.get_global_rank(group, src) if group is not None else src
+        head = pt.zeros(2, dtype=pt.int64, device="cpu" if on_host else dev)
+        if dist.get_rank(group) == src:
+            head[0], head[1] = tables.n, tables.k
+        dist.broadcast(head, src=root, group=group)
+        n, k = int(head[0]), int(head[1])
+        if dist.get_rank(group) != src:
+            tables = cls.__new__(cls)
+            tables.n, tables.k, tables._inflight = n, k, []
+            tables.idx = pt.empty((n, k), dtype=pt.int32, device=dev)
+            tables.w64 = pt.empty((n, k), dtype=pt.float64, device=dev)
+            tables.idx_sorted = pt.empty((n, k), dtype=pt.int32, device=dev)
+            tables.w32_sorted = pt.empty((n, k), dtype=pt.float32, device=dev)
+            tables.w64_sorted = pt.empty((n, k), dtype=pt.float64, device=dev)
+            tables.out_row = pt.empty((n,), dtype=pt.int32, device=dev)
+        for name in ("idx", "w64", "idx_sorted", "w32_sorted", "w64_sorted", "out_row"):
+            t = getattr(tables, name)
+            if on_host:
+                h = t.cpu()
+                dist.broadcast(h, src=root, group=group)
+                t.copy_(h)
+            else:
+                dist.broadcast(t, src=root, group=group)
+        tables._rows_unique = None
+        return tables
 
 
 class ExportData:
     def __init__(self, s_cube, write_new_file_for_each_field: bool = False, n_jobs: int = None,
                  n_neighbors: int = None, interpolate_at_vertices: bool = False, write_times: Union[list, str] = None,
                  append_existing: bool = False, out_dtype=None, device=None, write_files: bool = True,
-                 stream_host: bool = True):
+                 stream_host: bool = True, async_host: bool = False):
+        """
+        Arguments up to ``append_existing`` as in the reference (export.py:41-72). Extensions: ``out_dtype``
+        (``torch.float64`` = the reference's result dtype), ``device``, ``write_files=False`` (keep the interpolated
+        fields, write nothing), ``stream_host`` (pipelined H2D / kernel / D2H for host batches) and ``async_host``:
+        by default ``export()`` returns once the device has finished READING the caller's host batch and every batch
+        gets a fresh pinned result tensor (the reference's semantics: the caller may refill ``data`` and keep results);
+        ``async_host=True`` only enqueues and re-uses one pinned result buffer per (field, shape) -- the caller must
+        not touch ``data`` or rely on an earlier result before ``synchronize()``.
+        """
         _lib.require_cuda()
         self._device = pt.device(device) if device is not None else pt.device("cuda", pt.cuda.current_device())
         self._interpolate_at_vertices = interpolate_at_vertices
@@ -314,6 +321,7 @@ class ExportData:
         self._chunk_size = None
         self.metric_on_grid = None
         self._stream_host = stream_host          # host batches: pipelined pitched copies
+        self._async_host = async_host
         self._stream_min_elements = 1 << 22
         self._host_buffers = {}
 
@@ -375,6 +383,12 @@ class ExportData:
             if self._interpolate_at_vertices:
                 self._interpolated_fields.vertices = self._tables_vertices.interpolate_host(
                     _data, out=self._host_buffer("vertices", self._tables_vertices.n, _data), sync=False)
+            if not self._async_host:
+                # the caller's pinned tensor is read in place by the copy engine: hand control back only when those
+                # reads are done (the result copies of this batch still overlap whatever the caller does next)
+                for tables in (self._tables_centers, self._tables_vertices):
+                    if tables is not None:
+                        tables.wait_input()
         else:
             d = self._stage(_data)
             out_dtype = self._out_dtype
@@ -387,7 +401,10 @@ class ExportData:
         self._snapshot_counter += _data.size(-1)
 
     def _host_buffer(self, where: str, n_rows: int, data: pt.Tensor) -> pt.Tensor:
-        """Pinned result buffer of the streamed path, re-used while field name and batch shape stay the same."""
+        """Pinned result buffer of the streamed path: a fresh tensor per batch (pinned blocks are recycled by torch's
+        caching host allocator once the caller drops them); ``async_host``: one buffer per (field, shape), re-used."""
+        if not self._async_host:
+            return None
         key = (where, self._field_name, n_rows, data.size(1), data.size(2))
         buf = self._host_buffers.get(key)
         if buf is None:

@@ -1,13 +1,70 @@
 """
-Device gather + weighted-sum interpolation (host wrapper around ``s3_interp_gather``).
+Device gather + weighted-sum interpolation (host wrapper around ``s3_interp_gather_strided``).
 
 ``interpolate_data`` keeps the reference's signature (sparseSpatialSampling/export.py:446-468).
+
+Layout in HBM. The kernel reads the reference's ``[N, D, T]`` snapshot batches (T contiguous) through explicit strides,
+so any view whose last dimension is contiguous is interpolated in place. It is built for rows whose pitch is a multiple
+of 128 bytes: ``alloc_snapshots`` / ``to_pitched`` give such tensors (``[N, D, T]`` views of a ``[N, D, Tp]``
+allocation, ``Tp`` = T rounded up to 32 fp32 values), the streamed host path (``KnnTables.interpolate_host``) stages
+its windows that way by construction.
 """
 import torch as pt
 
 from . import _lib
 
 _DT = {pt.float32: _lib.S3_F32, pt.float64: _lib.S3_F64}
+LINE_BYTES = 128
+
+
+def pitched_columns(n_cols: int, dtype=pt.float32) -> int:
+    """Columns per row so that the row pitch is a multiple of a 128-byte cache line."""
+    per_line = LINE_BYTES // pt.empty((), dtype=dtype).element_size()
+    return (int(n_cols) + per_line - 1) // per_line * per_line
+
+
+def alloc_snapshots(n_rows: int, n_comp: int, n_cols: int, dtype=pt.float32, device=None, zero: bool = False) -> pt.Tensor:
+    """``[n_rows, n_comp, n_cols]`` view with 128-byte aligned component rows (the layout the gather kernel is built for)."""
+    tp = pitched_columns(n_cols, dtype)
+    make = pt.zeros if zero else pt.empty
+    return make((n_rows, n_comp, tp), dtype=dtype, device=device)[:, :, :n_cols]
+
+
+def to_pitched(data: pt.Tensor) -> pt.Tensor:
+    """Copy of a ``[N, D, T]`` / ``[N, T]`` device tensor in the pitched layout (no copy if it already is)."""
+    if data.dim() == 2:
+        return to_pitched(data.unsqueeze(1)).squeeze(1)
+    if is_pitched(data):
+        return data
+    out = alloc_snapshots(data.size(0), data.size(1), data.size(2), data.dtype, data.device)
+    out.copy_(data)
+    return out
+
+
+def is_pitched(data: pt.Tensor) -> bool:
+    es = data.element_size()
+    return (data.stride(-1) == 1 and all((s * es) % LINE_BYTES == 0 for s in data.stride()[:-1])
+            and data.data_ptr() % 16 == 0)
+
+
+def _rows_view(t: pt.Tensor):
+    """(tensor, n_comp, n_cols, row_stride, comp_stride) of a ``[N, ...]`` tensor whose last dimension is contiguous;
+    anything the kernel cannot address through two strides is made dense first."""
+    if t.dim() == 1:
+        t = t.unsqueeze(1)
+    if t.dim() == 2:
+        if t.stride(1) != 1 and t.size(1) > 1:
+            t = t.contiguous()
+        return t, 1, t.size(1), (t.stride(0) if t.size(0) > 1 else t.size(1)), t.size(1)
+    if t.dim() > 3 or (t.stride(-1) != 1 and t.size(-1) > 1):
+        t = t.contiguous().reshape(t.size(0), -1, t.size(-1)) if t.dim() > 3 else t.contiguous()
+    n, d, c = t.shape
+    comp_stride = t.stride(1) if d > 1 else c
+    row_stride = t.stride(0) if n > 1 else max((d - 1) * comp_stride + c, 1)
+    if comp_stride < c or row_stride < (d - 1) * comp_stride + c:          # overlapping / expanded views
+        t = t.contiguous()
+        comp_stride, row_stride = c, d * c
+    return t, d, c, row_stride, comp_stride
 
 
 def interp_gather(data: pt.Tensor, idx: pt.Tensor, weights: pt.Tensor, out: pt.Tensor = None,
@@ -15,31 +72,35 @@ def interp_gather(data: pt.Tensor, idx: pt.Tensor, weights: pt.Tensor, out: pt.T
     """
     ``out[c] = sum_j weights[c, j] * data[idx[c, j]]`` on the device.
 
-    :param data: CUDA tensor ``[N, ...]`` (fp32 or fp64), contiguous; trailing dims are flattened into one row
+    :param data: CUDA tensor ``[N, T]`` / ``[N, D, T]`` (fp32 or fp64); any row / component stride, T contiguous
     :param idx: CUDA int32 ``[Nc, k]``
     :param weights: CUDA ``[Nc, k]``; fp32 for the fp32 fast path, fp64 for fp64 output
+    :param out: optional result tensor ``[Nc, ...]`` of the same trailing shape (may be a pitched view)
     :param out_row: optional CUDA int32 ``[Nc]``, destination row of each processed cell
     """
     _lib.require_cuda()
     lib = _lib.load()
     assert data.is_cuda and idx.is_cuda and weights.is_cuda
     assert idx.dtype == pt.int32 and idx.dim() == 2
-    data = data.contiguous()
     n_src = data.size(0)
-    row_len = data.numel() // max(n_src, 1)
     n_cells, k = idx.shape
     if out_dtype is None:
         out_dtype = pt.float32 if (data.dtype == pt.float32 and weights.dtype == pt.float32) else pt.float64
     want_w = pt.float32 if out_dtype == pt.float32 else pt.float64
     if weights.dtype != want_w:
         weights = weights.to(want_w)
+    shape_out = (n_cells,) + tuple(data.shape[1:])
+    d, n_comp, n_cols, row_stride, comp_stride = _rows_view(data)
     if out is None:
-        out = pt.empty((n_cells,) + tuple(data.shape[1:]), dtype=out_dtype, device=data.device)
-    assert out.is_contiguous() and out.dtype == out_dtype
+        out = pt.empty(shape_out, dtype=out_dtype, device=data.device)
+    assert out.dtype == out_dtype and tuple(out.shape) == shape_out, (out.dtype, tuple(out.shape), shape_out)
+    o, o_comp, o_cols, o_row_stride, o_comp_stride = _rows_view(out)
+    assert o.data_ptr() == out.data_ptr(), "the result tensor must have a contiguous last dimension and simple strides"
     with pt.cuda.device(data.device):
-        _lib.check(lib.s3_interp_gather(_lib.ptr(data), _DT[data.dtype], n_src, row_len, _lib.ptr(idx.contiguous()),
-                                        _lib.ptr(weights.contiguous()), n_cells, k, _lib.ptr(out_row), _lib.ptr(out),
-                                        _DT[out_dtype], _lib.stream_ptr()))
+        _lib.check(lib.s3_interp_gather_strided(
+            _lib.ptr(d, strided=True), _DT[data.dtype], n_src, n_comp, n_cols, row_stride, comp_stride,
+            _lib.ptr(idx.contiguous()), _lib.ptr(weights.contiguous()), n_cells, k, _lib.ptr(out_row),
+            _lib.ptr(o, strided=True), _DT[out_dtype], o_row_stride, o_comp_stride, _lib.stream_ptr()))
     return out
 
 
@@ -66,102 +127,3 @@ def interpolate_data(weights: pt.Tensor, idx_weights: pt.Tensor, data: pt.Tensor
         d = d.to(pt.float64 if out_dtype == pt.float64 else pt.float32)
     out = interp_gather(d, i, w, out_dtype=out_dtype)
     return out if src_device.type == "cuda" else out.to(src_device)
-
-
-class GroupTables:
-    """
-    Tables of the grouped interpolation kernel (``s3_interp_groups_build`` / ``s3_interp_grouped``): for every group of
-    consecutive cells (processing order; group size ``s3_interp_group_size()`` = 4) the distinct source rows of the
-    group, a membership mask and one weight per (row, cell). Built once per KNN cache; a warp then loads every distinct
-    row once for all cells of its group instead of once per (cell, neighbour) reference.
-    """
-
-    def __init__(self, idx_sorted: pt.Tensor, w32_sorted: pt.Tensor):
-        _lib.require_cuda()
-        lib = _lib.load()
-        dev = idx_sorted.device
-        assert idx_sorted.dtype == pt.int32 and w32_sorted.dtype == pt.float32
-        self.n_cells, self.k = idx_sorted.shape
-        self.group = int(lib.s3_interp_group_size())
-        self.n_groups = (self.n_cells + self.group - 1) // self.group
-        cap = self.group * self.k
-        self.cnt = pt.zeros((max(self.n_groups, 1),), dtype=pt.int32, device=dev)
-        self.ent = pt.empty((max(self.n_groups, 1), cap, 2), dtype=pt.int32, device=dev)
-        self.wts = pt.empty((max(self.n_groups, 1), cap, 4), dtype=pt.float32, device=dev)
-        with pt.cuda.device(dev):
-            _lib.check(lib.s3_interp_groups_build(_lib.ptr(idx_sorted.contiguous()), _lib.ptr(w32_sorted.contiguous()),
-                                                  self.n_cells, self.k, _lib.ptr(self.cnt), _lib.ptr(self.ent),
-                                                  _lib.ptr(self.wts), _lib.stream_ptr()))
-
-    @property
-    def rows_per_cell(self) -> float:
-        """Distinct rows loaded per cell (k without grouping)."""
-        return float(self.cnt.sum().item()) / max(self.n_cells, 1)
-
-    def interpolate(self, data: pt.Tensor, out: pt.Tensor = None, out_row: pt.Tensor = None) -> pt.Tensor:
-        lib = _lib.load()
-        assert data.is_cuda and data.dtype == pt.float32
-        data = data.contiguous()
-        n_src = data.size(0)
-        row_len = data.numel() // max(n_src, 1)
-        if out is None:
-            out = pt.empty((self.n_cells,) + tuple(data.shape[1:]), dtype=pt.float32, device=data.device)
-        assert out.is_contiguous() and out.dtype == pt.float32
-        with pt.cuda.device(data.device):
-            _lib.check(lib.s3_interp_grouped(_lib.ptr(data), n_src, row_len, _lib.ptr(self.cnt), _lib.ptr(self.ent),
-                                             _lib.ptr(self.wts), self.n_cells, self.k, _lib.ptr(out_row), _lib.ptr(out),
-                                             _lib.S3_F32, _lib.stream_ptr()))
-        return out
-
-
-class StagedTiles:
-    """
-    Tile structures of the staged interpolation kernel (``s3_interp_tiles_build`` / ``s3_interp_staged``): for every
-    tile of 32 consecutive cells (processing order) the ascending list of unique source rows and the position of
-    every (cell, neighbour) reference in it. Built once per KNN cache.
-    """
-    TILE = 32
-
-    def __init__(self, idx_sorted: pt.Tensor, w32_sorted: pt.Tensor):
-        _lib.require_cuda()
-        lib = _lib.load()
-        dev = idx_sorted.device
-        self.n_cells, self.k = idx_sorted.shape
-        self.n_tiles = (self.n_cells + self.TILE - 1) // self.TILE
-        cap = self.TILE * self.k
-        self.rows = pt.empty((max(self.n_tiles, 1), cap), dtype=pt.int32, device=dev)
-        self.nrows = pt.zeros((max(self.n_tiles, 1),), dtype=pt.int32, device=dev)
-        self.lidx = pt.empty((max(self.n_tiles, 1), cap), dtype=pt.uint16, device=dev)
-        self.w = pt.zeros((max(self.n_tiles, 1) * self.TILE, self.k), dtype=pt.float32, device=dev)
-        self.w[:self.n_cells] = w32_sorted
-        with pt.cuda.device(dev):
-            _lib.check(lib.s3_interp_tiles_build(_lib.ptr(idx_sorted.contiguous()), self.n_cells, self.k,
-                                                 _lib.ptr(self.rows), _lib.ptr(self.nrows), _lib.ptr(self.lidx),
-                                                 _lib.stream_ptr()))
-        self.max_rows = int(self.nrows.max().item()) if self.n_tiles else 1
-        self.total_rows = int(self.nrows.sum().item()) if self.n_tiles else 0
-
-    def interpolate(self, data: pt.Tensor, out: pt.Tensor = None, out_row: pt.Tensor = None,
-                    chunk_cols: int = 256, pipelined: bool = False, stage_rows: int = 0, n_ctas: int = 0,
-                    gather4: bool = True) -> pt.Tensor:
-        lib = _lib.load()
-        assert data.is_cuda and data.dtype == pt.float32
-        data = data.contiguous()
-        n_src = data.size(0)
-        row_len = data.numel() // max(n_src, 1)
-        if out is None:
-            out = pt.empty((self.n_cells,) + tuple(data.shape[1:]), dtype=pt.float32, device=data.device)
-        if pipelined:
-            with pt.cuda.device(data.device):
-                _lib.check(lib.s3_interp_pipelined(_lib.ptr(data), n_src, row_len, _lib.ptr(self.rows),
-                                                   _lib.ptr(self.nrows), _lib.ptr(self.lidx), _lib.ptr(self.w),
-                                                   self.n_cells, self.k, self.max_rows, int(chunk_cols),
-                                                   int(stage_rows), int(n_ctas), int(gather4), _lib.ptr(out_row), _lib.ptr(out),
-                                                   _lib.stream_ptr()))
-            return out
-        with pt.cuda.device(data.device):
-            _lib.check(lib.s3_interp_staged(_lib.ptr(data), n_src, row_len, _lib.ptr(self.rows), _lib.ptr(self.nrows),
-                                            _lib.ptr(self.lidx), _lib.ptr(self.w), self.n_cells, self.k, self.max_rows,
-                                            int(chunk_cols), _lib.ptr(out_row), _lib.ptr(out), _lib.stream_ptr()))
-        return out
-

@@ -58,7 +58,7 @@ def test_invalid_arguments_return_status_codes(cuda):
     assert rc != 0 and lib.s3_last_error()
     _lib.check(lib.s3_knn_free(h))
     # unknown tuning key, selection of more cells than exist, bad SVD method
-    assert lib.s3_set_tuning(999, 1) != 0
+    assert lib.s3x_tune(999, 1) != 0
     g = pt.rand(4, dtype=pt.float64, device="cuda")
     f = pt.ones(4, dtype=pt.uint8, device="cuda")
     o = pt.empty(8, dtype=pt.int64, device="cuda")
@@ -68,7 +68,7 @@ def test_invalid_arguments_return_status_codes(cuda):
     gm = pt.empty((4, 4), dtype=pt.float64, device="cuda")
     assert lib.s3_svd_gram(_lib.ptr(a), _lib.ptr(m), _lib.ptr(m), 1, 4, 4, 7, _lib.ptr(gm), _lib.stream_ptr()) != 0
     with pytest.raises(_lib.S3Error):
-        _lib.check(lib.s3_set_tuning(999, 1))
+        _lib.tune(999, 1)
 
 
 def test_svd_of_tiny_and_single_snapshot_matrices(cuda):

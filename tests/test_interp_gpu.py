@@ -75,51 +75,6 @@ def test_reference_signature_interpolate_data(cuda):
     assert np.array_equal(out.numpy(), orc.interpolate(w, idx.astype(np.int64), data))
 
 
-@pytest.mark.parametrize("N,Nc,k,D,T,chunk", [
-    (5000, 1777, 8, 1, 1000, 256), (5000, 1000, 8, 2, 500, 128), (3000, 515, 26, 3, 64, 256), (2000, 33, 26, 1, 8, 128),
-    (100, 1, 8, 1, 4, 256), (4000, 2049, 5, 1, 128, 128), (60000, 3000, 26, 1, 260, 256),
-])
-def test_staged_kernel_equals_direct_kernel(cuda, N, Nc, k, D, T, chunk):
-    # the TMA-staged kernel accumulates in the same order as the direct one -> bit-identical fp32 results,
-    # and both are within the stated tolerance of the oracle
-    from sparsespatialsampling_b200.interpolate import interp_gather, StagedTiles
-    data, idx, w = _case(N, Nc, k, D, T, N + Nc + k)
-    if N == 60000:                                   # scattered references: more unique rows than the staging buffer
-        pass
-    else:                                            # clustered references: heavy row sharing inside a tile
-        base = (np.arange(Nc)[:, None] * 3) % max(N - 64, 1)
-        idx = (base + np.random.default_rng(1).integers(0, 48, (Nc, k))).astype(np.int32)
-    d = pt.from_numpy(data).cuda()
-    i = pt.from_numpy(idx).cuda()
-    wt = pt.from_numpy(w).float().cuda()
-    direct = interp_gather(d, i, wt)
-    tiles = StagedTiles(i, wt)
-    staged = tiles.interpolate(d, chunk_cols=chunk)
-    assert pt.equal(staged, direct)
-    for stage_rows, n_ctas, g4 in [(0, 0, False), (24, 3, False), (7, 148, False), (0, 0, True), (24, 5, True),
-                                   (8, 148, True)]:     # pipelined persistent variant, incl. row overflow
-        piped = tiles.interpolate(d, chunk_cols=chunk, pipelined=True, stage_rows=stage_rows, n_ctas=n_ctas,
-                                  gather4=g4)
-        assert pt.equal(piped, direct), (stage_rows, n_ctas, g4)
-    ref = orc.interpolate(w, idx.astype(np.int64), data)
-    scale = np.abs(data[idx]).max(axis=1)
-    assert (np.abs(staged.cpu().numpy() - ref) <= RTOL_F32 * np.maximum(scale, 1e-30)).all()
-    # permuted destination rows
-    perm = pt.randperm(Nc, device="cuda").to(pt.int32)
-    out = pt.zeros_like(direct)
-    tiles.interpolate(d, out=out, out_row=perm, chunk_cols=chunk)
-    assert pt.equal(out[perm.long()], direct)
-    # tile tables: every reference resolves to its source row
-    rows = tiles.rows.cpu().numpy().reshape(tiles.n_tiles, -1)
-    lidx = tiles.lidx.cpu().numpy().astype(np.int64).reshape(tiles.n_tiles, 32, k)
-    for t in range(0, tiles.n_tiles, max(1, tiles.n_tiles // 7)):
-        nc = min(32, Nc - 32 * t)
-        got = rows[t][lidx[t, :nc]]
-        assert np.array_equal(got, idx[32 * t:32 * t + nc])
-        nr = int(tiles.nrows[t])
-        assert np.array_equal(rows[t][:nr], np.unique(idx[32 * t:32 * t + nc]))
-
-
 @pytest.mark.parametrize("D,T,chunk", [(1, 1000, 256), (2, 300, 128), (3, 77, 32), (1, 64, None)])
 def test_streamed_host_path_equals_resident_path(cuda, D, T, chunk):
     """Pipelined host -> device -> host export over windows of the time axis (pitched copies) == one resident launch."""
@@ -179,69 +134,109 @@ def _local_case(N, Nc, k, D, T, seed):
 
 
 @pytest.mark.parametrize("N,Nc,k,D,T", [
-    (5000, 1777, 8, 1, 1000), (5000, 1002, 8, 2, 500), (3000, 515, 26, 3, 64), (2000, 101, 8, 1, 300),
-    (2000, 33, 26, 1, 8), (100, 1, 8, 1, 4), (4000, 2049, 5, 1, 128), (3000, 64, 64, 1, 256),
+    (5000, 1777, 8, 1, 1000), (5000, 1002, 8, 2, 500), (3000, 515, 26, 3, 64), (2000, 101, 8, 1, 301),
+    (2000, 33, 26, 1, 7), (100, 1, 8, 1, 4), (4000, 2049, 5, 1, 125), (3000, 64, 64, 2, 250),
 ])
-def test_grouped_kernel_within_tolerance(cuda, N, Nc, k, D, T):
-    # s3_interp_grouped: a warp interpolates 4 consecutive cells and loads the distinct rows of the group once
-    from sparsespatialsampling_b200.interpolate import GroupTables, interp_gather
+def test_pitched_layout_equals_dense_layout(cuda, N, Nc, k, D, T):
+    """Rows padded to a multiple of 128 bytes (the layout the kernel is built for), as source, as result and both:
+    bit-identical to the dense launch -- including T % 4 != 0, where the dense layout has to take the scalar path."""
+    from sparsespatialsampling_b200.interpolate import interp_gather, alloc_snapshots, to_pitched, is_pitched
     data, idx, w = _local_case(N, Nc, k, D, T, N + Nc + k)
-    ref = orc.interpolate(w, idx.astype(np.int64), data)
-    d_data, d_idx, d_w = pt.from_numpy(data).cuda(), pt.from_numpy(idx).cuda(), pt.from_numpy(w).float().cuda()
-    groups = GroupTables(d_idx, d_w)
-    assert groups.rows_per_cell <= k
-    if Nc >= 100:
-        assert groups.rows_per_cell < 0.9 * k                   # the sliding-window case does share rows
-    perm = pt.randperm(Nc, device="cuda").to(pt.int32)
-    out = groups.interpolate(d_data, out_row=perm)
-    assert out.dtype == pt.float32 and tuple(out.shape) == (Nc, D, T)
-    got = out.cpu().numpy().astype(np.float64)[perm.cpu().numpy().astype(np.int64)]     # row perm[c] holds cell c
-    scale = np.abs(data[idx]).max(axis=1)
-    err = np.abs(got - ref)
-    assert (err <= RTOL_F32 * np.maximum(scale, 1e-30)).all(), err.max()
-    direct = interp_gather(d_data, d_idx, d_w).cpu().numpy().astype(np.float64)
-    assert (np.abs(got - direct) <= 2 * RTOL_F32 * np.maximum(scale, 1e-30)).all()
+    d_dense = pt.from_numpy(data).cuda()
+    d_idx, d_w = pt.from_numpy(idx).cuda(), pt.from_numpy(w).float().cuda()
+    want = interp_gather(d_dense, d_idx, d_w)
+    d_pit = to_pitched(d_dense)
+    assert is_pitched(d_pit) and (d_pit.stride(1) * 4) % 128 == 0 and pt.equal(d_pit, d_dense)
+    assert pt.equal(interp_gather(d_pit, d_idx, d_w), want)
+    out = alloc_snapshots(Nc, D, T, device="cuda", zero=True)
+    interp_gather(d_pit, d_idx, d_w, out=out)
+    assert pt.equal(out, want)
+    assert float(out._base.abs().sum() - out.abs().sum()) == 0.0          # nothing written into the padding
+    out2 = alloc_snapshots(Nc, D, T, device="cuda")
+    interp_gather(d_dense, d_idx, d_w, out=out2)
+    assert pt.equal(out2, want)
+    # reference dtype on the pitched layout: bit-exact against the oracle
+    got64 = interp_gather(d_pit, d_idx, pt.from_numpy(w).cuda(), out_dtype=pt.float64)
+    assert np.array_equal(got64.cpu().numpy(), orc.interpolate(w, idx.astype(np.int64), data))
 
 
-def test_grouped_kernel_does_not_leak_rows_between_cells(cuda):
-    # a non-finite value in a row used by ONE cell of a group must not reach the other cells of the group, and a row
-    # listed twice for one cell contributes with the sum of its weights
-    from sparsespatialsampling_b200.interpolate import GroupTables
-    N, k, T = 64, 8, 128
-    rng = np.random.default_rng(3)
-    data = rng.standard_normal((N, 1, T)).astype(np.float32)
-    idx = np.stack([np.arange(8) + 2 * c for c in range(6)]).astype(np.int32)           # cells 0..5, overlapping rows
-    idx[1, 3] = idx[1, 2]                                                             # duplicate neighbour in cell 1
-    w = rng.random((6, k))
-    w /= w.sum(1, keepdims=True)
-    data[0, 0, 5] = np.inf                                                            # row 0: cell 0 only
-    data[1, 0, 9] = np.nan                                                            # row 1: cell 0 only
-    out = GroupTables(pt.from_numpy(idx).cuda(), pt.from_numpy(w).float().cuda()).interpolate(
-        pt.from_numpy(data).cuda()).cpu().numpy()
-    assert np.isinf(out[0, 0, 5]) and np.isnan(out[0, 0, 9])
-    assert np.isfinite(out[1:]).all()
-    ref = orc.interpolate(w, idx.astype(np.int64), data)
-    finite = np.isfinite(ref)
-    assert np.allclose(out[finite], ref[finite], rtol=0, atol=1e-5 * np.abs(data[np.isfinite(data)]).max())
+@pytest.mark.parametrize("offset", [4, 8, 20, 28, 3])
+def test_time_window_views_with_a_common_line_offset(cuda, offset):
+    """A window ``data[:, :, t0:t1]`` of a pitched batch: every row starts `t0` columns into a 128-byte line; the kernel
+    shortens its first step so that the following ones are line aligned. Odd offsets take the scalar path."""
+    from sparsespatialsampling_b200.interpolate import interp_gather, alloc_snapshots
+    data, idx, w = _local_case(3000, 700, 8, 2, 600, offset)
+    full = alloc_snapshots(3000, 2, 600, device="cuda")
+    full.copy_(pt.from_numpy(data))
+    d_idx, d_w = pt.from_numpy(idx).cuda(), pt.from_numpy(w).float().cuda()
+    for t1 in (600, 517, offset + 1):
+        view = full[:, :, offset:t1]
+        want = interp_gather(view.contiguous(), d_idx, d_w)
+        assert pt.equal(interp_gather(view, d_idx, d_w), want), t1
+        out = alloc_snapshots(700, 2, 600, device="cuda", zero=True)
+        interp_gather(view, d_idx, d_w, out=out[:, :, offset:t1])
+        assert pt.equal(out[:, :, offset:t1], want) and float(out[:, :, :offset].abs().sum()) == 0.0
+        assert float(out[:, :, t1:].abs().sum()) == 0.0
 
 
-def test_knn_tables_grouped_mode_equals_direct_mode(cuda):
-    from sparsespatialsampling_b200.export import KnnTables
-    from sparsespatialsampling_b200.knn import KnnIndex
-    rng = np.random.default_rng(11)
-    pts = pt.from_numpy(rng.random((6000, 2)))
-    centers = pt.from_numpy(rng.random((1501, 2)))
-    tables = KnnTables(KnnIndex(pts.cuda()), centers, 8)
-    data = pt.from_numpy(rng.standard_normal((6000, 2, 200)).astype(np.float32)).cuda()
-    tables.mode = "direct"
-    a = tables.interpolate(data, pt.float32)
-    tables.mode = "grouped"
-    b = tables.interpolate(data, pt.float32)
-    assert tables.groups.rows_per_cell < 8
-    scale = float(data.abs().max())
-    assert float((a - b).abs().max()) <= 2 * RTOL_F32 * scale
-    # streamed host path in grouped mode (DMA and row-gather ingest) against the resident result
-    host = data.cpu().pin_memory()
-    for gather in (False, True):
-        c = tables.interpolate_host(host, chunk_snapshots=64, gather=gather)
-        assert pt.equal(c, b.cpu()), gather
+@pytest.mark.parametrize("tune", ["1=4", "1=16", "2=1", "2=2", "3=0", "3=1", "4=256", "4=128,2=2", "6=1", "6=1,2=2",
+                                  "7=4", "7=4,3=1,2=2", "6=1,7=4"])
+def test_launch_variants_are_bit_identical(cuda, tune):
+    """The launch knobs of the A/B harness (warps per CTA, column vectors per step, shared-memory pairs, column
+    windows, 256-bit loads, neighbour-loop batching) change scheduling only: same sums in the same order."""
+    from sparsespatialsampling_b200 import _lib
+    from sparsespatialsampling_b200.interpolate import interp_gather, to_pitched
+    cases = [_local_case(3000, 900, 8, 1, 1000, 1), _local_case(3000, 300, 26, 2, 333, 2)]
+    defaults = {1: 8, 2: 0, 3: -1, 4: 0, 6: 0, 7: 1}
+    want = []
+    for data, idx, w in cases:
+        want.append(interp_gather(to_pitched(pt.from_numpy(data).cuda()), pt.from_numpy(idx).cuda(),
+                                  pt.from_numpy(w).float().cuda()))
+    try:
+        for kv in tune.split(","):
+            key, value = kv.split("=")
+            _lib.tune(int(key), int(value))
+        for (data, idx, w), ref in zip(cases, want):
+            for layout in (to_pitched, lambda x: x):
+                got = interp_gather(layout(pt.from_numpy(data).cuda()), pt.from_numpy(idx).cuda(),
+                                    pt.from_numpy(w).float().cuda())
+                assert pt.equal(got, ref)
+            got64 = interp_gather(pt.from_numpy(data).cuda(), pt.from_numpy(idx).cuda(), pt.from_numpy(w).cuda(),
+                                  out_dtype=pt.float64)
+            assert np.array_equal(got64.cpu().numpy(), orc.interpolate(w, idx.astype(np.int64), data))
+    finally:
+        for key, value in defaults.items():
+            _lib.tune(key, value)
+
+
+def test_streamed_export_hands_out_fresh_results_and_releases_the_input(cuda, tmp_path):
+    """export() of a pinned host batch must not return while the copy engine still reads the caller's tensor,
+    and a result kept from batch i must survive batch i+1 (the reference returns fresh tensors)."""
+    from sparsespatialsampling_b200.export import ExportData
+    rng = np.random.default_rng(5)
+    x = pt.from_numpy(rng.random((5000, 2)))
+
+    class _Grid:
+        pass
+    g = _Grid()
+    g.n_dimensions, g.faces, g.vertices, g.levels = 2, None, None, None
+    g.centers, g.metric, g.size_initial_cell = pt.from_numpy(rng.random((1500, 2))), pt.from_numpy(rng.random(5000)), 1.0
+    g.save_path, g.save_name, g.grid_name = str(tmp_path), "c", "grid"
+    a = pt.from_numpy(rng.standard_normal((5000, 1, 512)).astype(np.float32))
+    b = pt.from_numpy(rng.standard_normal((5000, 1, 512)).astype(np.float32))
+    exp = ExportData(g, write_times=[str(i) for i in range(1024)], write_files=False)
+    exp._stream_min_elements = 0
+    buf = a.clone().pin_memory()
+    exp.export(x, buf, "p", n_snapshots_total=1024)
+    first = exp._last_fields.centers                     # kept across the next batch
+    buf.copy_(b)                                         # refill the SAME pinned buffer, as a batch loop does
+    exp.export(x, buf, "p", n_snapshots_total=1024)
+    second = exp.interpolated_fields.centers
+    exp.synchronize()
+    ref = ExportData(g, write_times=[str(i) for i in range(1024)], write_files=False, stream_host=False)
+    ref.export(x, a, "p", n_snapshots_total=1024)
+    want_a = ref.interpolated_fields.centers.cpu()
+    ref.export(x, b, "p", n_snapshots_total=1024)
+    want_b = ref.interpolated_fields.centers.cpu()
+    assert first.data_ptr() != second.data_ptr()
+    assert pt.equal(first, want_a) and pt.equal(second, want_b)

@@ -32,7 +32,7 @@ def _low_rank_field(n_cells, t, n_modes, seed, d=None, noise=1e-3):
 def test_gram_matches_fp64(cuda, method, m, t):
     from sparsespatialsampling_b200 import svd, _lib
     # default: clusters of two CTAs sharing the B operand by TMA multicast; "-single-cta": one CTA per tile
-    _lib.check(_lib.load().s3_set_tuning(14, 0 if method.endswith("single-cta") else 1))
+    _lib.tune(14, 0 if method.endswith("single-cta") else 1)
     method = method.split("-")[0]
     a, area = _low_rank_field(m, t, 5, m + t)
     ref = orc.weighted_gram(a, area)
@@ -44,7 +44,7 @@ def test_gram_matches_fp64(cuda, method, m, t):
     scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
     tol = {"simt": 2e-5, "tc3": 5e-6, "tc": 3e-3}[method]
     # the mean is rounded to fp32 on both sides; fp32 products/accumulation inside a segment bound the rest
-    _lib.check(_lib.load().s3_set_tuning(14, 1))
+    _lib.tune(14, 1)
     assert (np.abs(g - ref) <= tol * scale + 1e-30).all(), float((np.abs(g - ref) / (scale + 1e-300)).max())
 
 
@@ -60,13 +60,13 @@ def test_gram_many_rows_segments_and_splits(cuda):
     scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
     try:
         for seg, flush in ((1, 1), (3, 5), (4, 32), (7, 1000), (8, 128)):
-            _lib.check(lib.s3_set_tuning(10, seg))
-            _lib.check(lib.s3_set_tuning(11, flush))
+            _lib.tune(10, seg)
+            _lib.tune(11, flush)
             g = svd.gram(ad, mean, vol, 1, "tc3").cpu().numpy()
             assert (np.abs(g - ref) <= 5e-6 * scale).all(), (seg, flush, float((np.abs(g - ref) / scale).max()))
     finally:
-        _lib.check(lib.s3_set_tuning(10, 8))
-        _lib.check(lib.s3_set_tuning(11, 128))
+        _lib.tune(10, 8)
+        _lib.tune(11, 128)
 
 
 @pytest.mark.parametrize("d", [None, 2, 3])
