@@ -20,9 +20,11 @@ from sparsespatialsampling_b200.export import KnnTables
 from sparsespatialsampling_b200.interpolate import alloc_snapshots
 from sparsespatialsampling_b200.knn import KnnIndex
 
-DEFAULTS = {1: 8, 2: 0, 3: -1, 4: 0, 5: -1, 6: 0, 7: 1}
-VARIANTS = ["", "3=1", "2=2", "2=2,3=1", "7=4", "7=4,3=1", "7=4,2=2", "6=1", "6=1,3=1", "6=1,7=4", "6=1,2=2",
-            "1=4", "1=16", "1=16,3=1", "4=256", "4=512", "4=256,3=1", "1=4,7=4", "5=0", "5=50"]
+DEFAULTS = {1: 8, 2: 0, 3: -1, 4: 0, 5: -1, 6: -1, 7: 1, 9: 1}
+VARIANTS = ["", "9=0", "9=0,6=0", "9=0,6=0,2=1", "6=-1,3=0", "2=2", "1=4", "1=16", "4=512", "7=4"]
+OLD_VARIANTS = ["", "7=2", "7=4", "2=2", "2=2,7=2", "6=1,3=1", "6=1,3=1,7=2", "8=2", "8=2,7=2", "8=2,7=4", "8=2,4=512",
+            "8=2,7=2,4=512", "8=4", "8=4,7=2", "8=4,4=512", "8=4,4=256", "8=4,1=4", "8=4,1=4,4=512", "8=2,1=4",
+            "8=2,1=16", "8=4,1=2,4=512"]
 
 
 def main():
@@ -30,6 +32,8 @@ def main():
     ap.add_argument("--variants", default="")
     ap.add_argument("--snapshots", type=int, default=1000)
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--layouts", default="pitched,dense")
     ap.add_argument("--k26", action="store_true", help="3-D style tables (k = 26) on a synthetic 3-D cloud instead of C2")
     args = ap.parse_args()
     dev = pt.device("cuda", 0)
@@ -71,12 +75,12 @@ def main():
         for kv in [t for t in var.split(",") if t]:
             key, val = kv.split("=")
             _lib.tune(int(key), int(val))
-        for layout in ("pitched", "dense"):
+        for layout in args.layouts.split(","):
             def step():
                 for comps in (1, 2):
                     d, o = fields[comps][layout]
                     tables.interpolate(d, pt.float32, out=o)
-            for _ in range(3):
+            for _ in range(args.warmup):
                 step()
             pt.cuda.synchronize()
             e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)

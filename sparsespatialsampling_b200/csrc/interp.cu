@@ -31,7 +31,8 @@ static int g_unroll = 0;           // key 2: column vectors per lane and step, 0
 static int g_pairs = -1;           // key 3: (idx, w) broadcast: 0 = SHFL, 1 = shared-memory pairs, -1 = by k
 static int g_chunk_cols = 0;       // key 4: columns per blockIdx.y window, 0 = whole row
 static int g_carveout = -1;        // key 5: shared-memory carve-out in percent, -1 = driver default
-static int g_wide = 0;             // key 6: 1 = 256-bit loads (fp32 in/out, row pitch multiple of 32 B)
+static int g_wide = -1;            // key 6: 256-bit loads (fp32 in/out, pointers and pitches multiples of 32 B): -1 = whenever possible
+static int g_dense = 1;            // key 9: 1 = dense fp32 batches with k <= 16 take interp_dense_kernel
 static int g_kunroll = 1;          // key 7: neighbour-loop unroll (row loads in flight per lane): 1 or 4
 extern int g_tc_seg_kblocks;
 extern int g_tc_flush_segments;
@@ -182,6 +183,48 @@ interp_warpcell_kernel(const Tin* __restrict__ data, const int32_t* __restrict__
     }
 }
 
+// Dense fp32 batches (row pitch = row length on both sides), the reference's own layout: the round-1 formulation of
+// the same loop, kept because ptxas schedules it best for k = 8 (four predicated row loads in flight at 32 registers
+// = 64 resident warps per SM; C2: 0.391 ms per step against 0.405-0.48 for the strided instantiations on this layout).
+__global__ void __launch_bounds__(512)
+interp_dense_kernel(const float* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
+                    const float* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
+                    float* __restrict__ out) {
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t cell = (int64_t)blockIdx.x * warps + warp;
+    if (cell >= n_cells) return;
+    int32_t idx_lo = 0, idx_hi = 0;
+    float w_lo = 0.f, w_hi = 0.f;
+    if (lane < k) { idx_lo = idx[cell * k + lane]; w_lo = w[cell * k + lane]; }
+    if (lane + 32 < k) { idx_hi = idx[cell * k + lane + 32]; w_hi = w[cell * k + lane + 32]; }
+    const int64_t orow = out_row ? (int64_t)out_row[cell] : cell;
+    float* o = out + orow * row_len;
+    constexpr int V = 4, STEP = 32 * V;
+    for (int64_t col0 = 0; col0 < row_len; col0 += (int64_t)STEP) {
+        float acc[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = 0.f;
+        for (int j = 0; j < k; ++j) {
+            const int32_t r = __shfl_sync(0xffffffffu, (j & 32) ? idx_hi : idx_lo, j & 31);
+            const float wj = __shfl_sync(0xffffffffu, (j & 32) ? w_hi : w_lo, j & 31);
+            const float* src = data + (int64_t)r * row_len + col0 + lane * V;
+            if (col0 + lane * V < row_len) {
+                const Vec<float, V> x = ld_vec<float, V>(src);
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc[e] = fmaf(wj, x.v[e], acc[e]);
+            }
+        }
+        const int64_t c = col0 + lane * V;
+        if (c < row_len) {
+            Vec<float, V> ov;
+#pragma unroll
+            for (int e = 0; e < V; ++e) ov.v[e] = acc[e];
+            *reinterpret_cast<Vec<float, V>*>(o + c) = ov;
+        }
+    }
+}
+
 template <typename Tin, typename Tw, typename Tout, int MODE>
 static int launch_interp(const void* data, const int32_t* idx, const void* w, int64_t n_cells, int k,
                          const int32_t* out_row, void* out, int n_comp, InterpGeom g, cudaStream_t stream) {
@@ -193,13 +236,28 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
     const bool vec_ok = ((uintptr_t)data % 16 == 0) && ((uintptr_t)out % (sizeof(Tout) * VFULL) == 0) &&
                         g.row_stride % VFULL == 0 && g.comp_stride % VFULL == 0 && g.out_row_stride % VFULL == 0 &&
                         g.out_comp_stride % VFULL == 0;
-    // column vectors per lane and step: measured best 1 for k = 8 (C2/C3), 2 for k = 26 (C4/C5); 0 = this rule
-    const int unroll = g_unroll != 0 ? g_unroll : (k > 16 ? 2 : 1);
-    const bool pairs = g_pairs >= 0 ? g_pairs != 0 : k > 16;
-    const bool wide = g_wide != 0 && vec_ok && MODE == 0 && std::is_same<Tin, float>::value &&
-                      std::is_same<Tout, float>::value && (uintptr_t)data % 32 == 0 && (uintptr_t)out % 32 == 0 &&
-                      g.row_stride % 8 == 0 && g.comp_stride % 8 == 0 && g.out_row_stride % 8 == 0 &&
-                      g.out_comp_stride % 8 == 0;
+    // Launch shape by measurement (C2 tables k = 8, T = 1000 and 3-D tables k = 26, T = 2000; scripts/interp_lab.py,
+    // profiles/r2_interp_lab.md): 256-bit row loads with the (index, weight) pairs in shared memory whenever pointers
+    // and pitches are 32-byte aligned (k = 8: 0.378 ms per C2 step on 128-byte pitched rows against 0.387 with two
+    // 128-bit vectors per lane and 0.46 with one; k = 26: 8.1-8.5 ms against 9.5-9.7), one column vector per lane for
+    // k <= 16 and two beyond, two 128-bit vectors otherwise.
+    const bool wide_ok = vec_ok && MODE == 0 && std::is_same<Tin, float>::value && std::is_same<Tout, float>::value &&
+                         (uintptr_t)data % 32 == 0 && (uintptr_t)out % 32 == 0 && g.row_stride % 8 == 0 &&
+                         g.comp_stride % 8 == 0 && g.out_row_stride % 8 == 0 && g.out_comp_stride % 8 == 0;
+    const bool wide = wide_ok && g_wide != 0;
+    const int unroll = g_unroll != 0 ? g_unroll : (wide ? (k > 16 ? 2 : 1) : 2);
+    const bool pairs = g_pairs >= 0 ? g_pairs != 0 : (wide || k > 16);
+    if constexpr (std::is_same<Tin, float>::value && std::is_same<Tout, float>::value && MODE == 0) {
+        if (g_dense && vec_ok && k <= 16 && n_comp == 1 && g.n_cols % 4 == 0 && g.row_stride == g.n_cols &&
+            g.out_row_stride == g.n_cols && g_chunk_cols == 0) {
+            interp_dense_kernel<<<(unsigned)blocks, warps * 32, 0, stream>>>(
+                reinterpret_cast<const float*>(data), g.n_cols, idx, reinterpret_cast<const float*>(w), n_cells, k,
+                out_row, reinterpret_cast<float*>(out));
+            S3_LAUNCH_CHECK();
+            note_launch(1);
+            return S3_OK;
+        }
+    }
     const int v = wide ? 8 : (vec_ok ? VFULL : 1);
     const int64_t step = (int64_t)32 * v * unroll;
     // all rows share their offset inside a 128-byte line when the pitches are multiples of 128 bytes: shorten the
@@ -264,7 +322,8 @@ extern "C" int s3x_tune(int key, int value) {
         case 3: S3_REQUIRE(value >= -1 && value <= 1, "s3x_tune: pairs must be -1 (by k), 0 or 1"); g_pairs = value; return S3_OK;
         case 4: S3_REQUIRE(value >= 0, "s3x_tune: window columns must be >= 0"); g_chunk_cols = value; return S3_OK;
         case 5: S3_REQUIRE(value >= -1 && value <= 100, "s3x_tune: carve-out must be -1 or 0..100"); g_carveout = value; return S3_OK;
-        case 6: S3_REQUIRE(value == 0 || value == 1, "s3x_tune: wide must be 0 or 1"); g_wide = value; return S3_OK;
+        case 6: S3_REQUIRE(value >= -1 && value <= 1, "s3x_tune: wide must be -1 (auto), 0 or 1"); g_wide = value; return S3_OK;
+        case 9: S3_REQUIRE(value == 0 || value == 1, "s3x_tune: dense kernel must be 0 or 1"); g_dense = value; return S3_OK;
         case 7: S3_REQUIRE(value == 1 || value == 4, "s3x_tune: neighbour-loop unroll must be 1 or 4"); g_kunroll = value; return S3_OK;
         case 10: S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3x_tune: K-blocks per TMEM segment must be >= 1"); g_tc_seg_kblocks = value; return S3_OK;
         case 11: S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3x_tune: segments per fp64 flush must be >= 1"); g_tc_flush_segments = value; return S3_OK;

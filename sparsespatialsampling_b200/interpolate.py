@@ -127,3 +127,4 @@ def interpolate_data(weights: pt.Tensor, idx_weights: pt.Tensor, data: pt.Tensor
         d = d.to(pt.float64 if out_dtype == pt.float64 else pt.float32)
     out = interp_gather(d, i, w, out_dtype=out_dtype)
     return out if src_device.type == "cuda" else out.to(src_device)
+
