@@ -10,10 +10,11 @@ I/O side of the export stage with the interface of the reference (sparseSpatialS
 and the same on-disk layout: ``grid/{centers,vertices,faces}``, ``constant/*``, ``data/<time>/<field>_{center,vertices}``
 (const.py:6-17, export.py:252-299).
 
-File I/O is outside the accelerated path: this module is plain host Python. The container is
-h5py when it can be imported; this image has no h5py, in which case the identical group/dataset tree is kept as nested
-dicts of tensors and stored with ``torch.save`` as ``<file>.pt`` -- the XDMF text is generated either way and refers to
-the HDF5 file name, exactly like the reference's.
+File I/O is outside the accelerated path: this module is plain host Python. The files are real
+HDF5: written through h5py when it can be imported, otherwise through ``h5lite`` -- a small pure-Python implementation of
+the subset of the HDF5 format that h5py's defaults produce (version-0 superblock, symbol-table groups, contiguous
+datasets), which also reads the reference's own output files. Data is appended to the file as it arrives (batch-wise
+exports cost I/O linear in their size, nothing is kept in memory).
 """
 import logging
 from os.path import join, isfile
@@ -22,6 +23,7 @@ from typing import List, Union
 import numpy as np
 import torch as pt
 
+from . import h5lite
 from .const import CONST, GRID, DATA, CENTERS, VERTICES, FACES
 
 logger = logging.getLogger(__name__)
@@ -32,60 +34,13 @@ try:                                    # pragma: no cover - depends on the imag
 except ImportError:                     # pragma: no cover
     h5py = None
     HAVE_H5PY = False
+FORCE_H5LITE = False                    # tests: exercise the built-in writer even when h5py is installed
 
 
 def _to_numpy(data):
     if isinstance(data, pt.Tensor):
         return data.detach().cpu().numpy()
     return np.asarray(data)
-
-
-class _TreeStore:
-    """Group/dataset tree with the small part of the h5py API used here, backed by ``torch.save``."""
-
-    def __init__(self, path: str, mode: str):
-        self._path = path + ".pt"
-        self._mode = mode
-        self.root = {}
-        if mode in ("r", "a", "r+"):
-            if isfile(self._path):
-                self.root = pt.load(self._path, weights_only=False)
-            elif mode != "a":
-                raise FileNotFoundError(self._path)
-
-    def _node(self, path: str, create: bool = False):
-        node = self.root
-        for part in [p for p in path.split("/") if p]:
-            if part not in node:
-                if not create:
-                    return None
-                node[part] = {}
-            node = node[part]
-        return node
-
-    def keys(self, path: str = "") -> List[str]:
-        node = self._node(path)
-        return sorted(node.keys()) if isinstance(node, dict) else []      # HDF5 iterates links in name order
-
-    def has(self, path: str) -> bool:
-        return self._node(path) is not None
-
-    def read(self, path: str) -> np.ndarray:
-        node = self._node(path)
-        if node is None or isinstance(node, dict):
-            raise KeyError(path)
-        return _to_numpy(node)
-
-    def write(self, group: str, name: str, data) -> bool:
-        node = self._node(group, create=True)
-        if name in node:
-            return False
-        node[name] = data.detach().cpu().clone() if isinstance(data, pt.Tensor) else data
-        return True
-
-    def close(self) -> None:
-        if self._mode != "r":
-            pt.save(self.root, self._path)
 
 
 class _H5Store:                         # pragma: no cover - needs h5py
@@ -104,6 +59,9 @@ class _H5Store:                         # pragma: no cover - needs h5py
     def read(self, path: str) -> np.ndarray:
         return self._file[path][()]
 
+    def shape(self, path: str) -> tuple:
+        return tuple(self._file[path].shape)
+
     def write(self, group: str, name: str, data) -> bool:
         grp = self._file.require_group(group)
         if name in grp:
@@ -115,11 +73,25 @@ class _H5Store:                         # pragma: no cover - needs h5py
         self._file.close()
 
 
+class _LiteStore:
+    """The same small API on top of ``h5lite.File`` (tensors are converted to numpy on the way in)."""
+
+    def __init__(self, path: str, mode: str):
+        self._file = h5lite.File(path, mode)
+        self.keys, self.has, self.read, self.shape = self._file.keys, self._file.has, self._file.read, self._file.shape
+
+    def write(self, group: str, name: str, data) -> bool:
+        return self._file.write(group, name, _to_numpy(data))
+
+    def close(self) -> None:
+        self._file.close()
+
+
 def _open_store(file_path: str, file_name: str, mode: str):
     full = join(file_path, file_name)
-    if HAVE_H5PY:                       # pragma: no cover
+    if HAVE_H5PY and not FORCE_H5LITE:  # pragma: no cover
         return _H5Store(full, mode)
-    return _TreeStore(full, mode)
+    return _LiteStore(full, mode)
 
 
 # ---------------------------------------------------------------------------------------------------- Dataloader
@@ -259,9 +231,6 @@ class Datawriter:
         self._n_cells = None
         self._closed = False
         self._store = _open_store(file_path, file_name, mode)
-        if not HAVE_H5PY:
-            logger.warning("h5py is not installed: writing the HDF5 tree as a torch file "
-                           f"{join(file_path, file_name)}.pt instead.")
 
     # ------------------------------------------------------------------ reference interface
     def write_data(self, name: str, data: any, group: str = CONST, time_step: Union[int, float, str] = None) -> None:
@@ -296,11 +265,6 @@ class Datawriter:
         if not self._closed:
             self._store.close()
             self._closed = True
-
-    @property
-    def tree(self):
-        """In-memory group/dataset tree (only when h5py is unavailable)."""
-        return getattr(self._store, "root", None)
 
     @property
     def mode(self) -> str:
@@ -342,11 +306,11 @@ class XDMFWriter:
         self._xdmf_file_name = f"{file_name.split('.h5')[0]}.xdmf"
         self._store = _open_store(file_path, file_name, "r")
         self._check_grid()
-        centers = self._store.read(f"{GRID}/{CENTERS}")
-        self._n_dimensions = centers.shape[-1]
-        self._n_cells = centers.shape[0]
-        self._n_faces = self._store.read(f"{GRID}/{FACES}").shape[0]
-        self._n_vertices = self._store.read(f"{GRID}/{VERTICES}").shape[0]
+        centers = self._store.shape(f"{GRID}/{CENTERS}")
+        self._n_dimensions = centers[-1]
+        self._n_cells = centers[0]
+        self._n_faces = self._store.shape(f"{GRID}/{FACES}")[0]
+        self._n_vertices = self._store.shape(f"{GRID}/{VERTICES}")[0]
         if mixed:
             self._grid_type = "Mixed"
         else:
@@ -398,7 +362,7 @@ class XDMFWriter:
             return ""
         out = []
         for k in self._store.keys(CONST):
-            shape = np.shape(self._store.read(f"{CONST}/{k}"))
+            shape = self._store.shape(f"{CONST}/{k}")
             if len(shape) and shape[0] in (self._n_cells, self._n_vertices):
                 out.append(self._attribute(k, f"{CONST}/{k}", shape))
         return "".join(out)
@@ -417,7 +381,7 @@ class XDMFWriter:
                 for k in self._store.keys(f"{DATA}/{t}"):
                     # fields are stored as <field_name>_<position>
                     name = "_".join(k.split("_")[:-1]) if len(k.split("_")) > 1 else k
-                    parts.append(self._attribute(name, f"{DATA}/{t}/{k}", np.shape(self._store.read(f"{DATA}/{t}/{k}"))))
+                    parts.append(self._attribute(name, f"{DATA}/{t}/{k}", self._store.shape(f"{DATA}/{t}/{k}")))
                 parts.append('</Grid>\n')
             parts.append('</Grid>\n</Domain>\n</Xdmf>')
         else:
