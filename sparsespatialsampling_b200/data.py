@@ -87,6 +87,17 @@ class _LiteStore:
         self._file.close()
 
 
+PART_FILES = "part_files"               # constant/part_files: newline-joined names of the other parts (UTF-8 bytes)
+
+
+def _read_part_files(store) -> List[str]:
+    """Names of the additional part files of a sharded export (``ExportData(distributed=True)``), [] otherwise."""
+    if not store.has(f"{CONST}/{PART_FILES}"):
+        return []
+    raw = bytes(np.asarray(store.read(f"{CONST}/{PART_FILES}"), dtype=np.uint8))
+    return [n for n in raw.decode("utf-8").split("\n") if n]
+
+
 def _open_store(file_path: str, file_name: str, mode: str):
     full = join(file_path, file_name)
     if HAVE_H5PY and not FORCE_H5LITE:  # pragma: no cover
@@ -108,6 +119,18 @@ class Dataloader:
     def _store(self):
         return _open_store(self._load_path, self._file_name, "r")
 
+    def _stores_by_time(self) -> dict:
+        """time step -> store that holds it (the file itself, then the parts of a sharded export in rank order)."""
+        if self._time_index is None:
+            main = self._store()
+            index = {}
+            for st in [main] + [_open_store(self._load_path, name, "r") for name in _read_part_files(main)]:
+                if st.has(DATA):
+                    for t in st.keys(DATA):
+                        index.setdefault(t, st)
+            self._time_index = index
+        return self._time_index
+
     def _reset(self) -> None:
         st = self._store()
         centers = st.read(f"{GRID}/{CENTERS}")
@@ -117,6 +140,7 @@ class Dataloader:
         except KeyError:
             logger.warning("Could not load initial cell size.")
         self._write_times = None
+        self._time_index = None
         self._weights = None
         self._levels = None
         self._metric = None
@@ -131,9 +155,9 @@ class Dataloader:
     @property
     def write_times(self) -> List[str]:
         if self._write_times is None:
-            st = self._store()
-            if st.has(DATA):
-                self._write_times = st.keys(DATA)
+            index = self._stores_by_time()
+            if index:
+                self._write_times = sorted(index.keys(), key=lambda s: s.encode("utf-8"))   # HDF5 link order
         return self._write_times
 
     @property
@@ -166,9 +190,9 @@ class Dataloader:
     @property
     def field_names(self) -> dict:
         if self._field_names is None:
-            st = self._store()
-            self._field_names = {t: [f.split("_")[0] for f in st.keys(f"{DATA}/{t}") if f.endswith("center")]
-                                 for t in st.keys(DATA)}
+            index = self._stores_by_time()
+            self._field_names = {t: [f.split("_")[0] for f in index[t].keys(f"{DATA}/{t}") if f.endswith("center")]
+                                 for t in (self.write_times or [])}
         return self._field_names
 
     @property
@@ -210,13 +234,13 @@ class Dataloader:
             write_times = [write_times]
         if isinstance(field_name, str):
             field_name = [field_name]
-        st = self._store()
+        index = self._stores_by_time()
         matrices = []
         for f in field_name:
-            first = st.read(f"{DATA}/{write_times[0]}/{f}_center")
+            first = index[write_times[0]].read(f"{DATA}/{write_times[0]}/{f}_center")
             dm = pt.zeros(tuple(first.shape) + (len(write_times),), dtype=self._dtype)
             for i, t in enumerate(write_times):
-                dm[..., i] = pt.from_numpy(np.array(st.read(f"{DATA}/{t}/{f}_center")))
+                dm[..., i] = pt.from_numpy(np.array(index[t].read(f"{DATA}/{t}/{f}_center")))
             matrices.append(dm)
         return matrices[0] if len(matrices) == 1 else matrices
 
@@ -255,6 +279,11 @@ class Datawriter:
         self.write_data(CENTERS, group=GRID, data=loader.vertices)
         self.write_data(VERTICES, group=GRID, data=loader.nodes)
         self.write_data(FACES, group=GRID, data=loader.faces)
+
+    def write_part_files(self, names: List[str]) -> None:
+        """Record the other part files of a sharded export (``constant/part_files``, newline-joined UTF-8 bytes)."""
+        raw = np.frombuffer("\n".join(names).encode("utf-8"), dtype=np.uint8)
+        self._store.write(CONST, PART_FILES, raw)
 
     def write_xdmf_file(self) -> None:
         logger.info(f"Writing XDMF file for file {self._file_name}")
@@ -305,6 +334,13 @@ class XDMFWriter:
         self._hdf_file_name = file_name
         self._xdmf_file_name = f"{file_name.split('.h5')[0]}.xdmf"
         self._store = _open_store(file_path, file_name, "r")
+        # sharded export: time steps live in the file itself or in one of its parts
+        self._time_files = {}
+        for name in [file_name] + _read_part_files(self._store):
+            st = self._store if name == file_name else _open_store(file_path, name, "r")
+            if st.has(DATA):
+                for t in st.keys(DATA):
+                    self._time_files.setdefault(t, (name, st))
         self._check_grid()
         centers = self._store.shape(f"{GRID}/{CENTERS}")
         self._n_dimensions = centers[-1]
@@ -338,8 +374,9 @@ class XDMFWriter:
                 f'{self._hdf_file_name}:/{GRID}/{VERTICES}\n'
                 f'</DataItem>\n</Geometry>\n')
 
-    def _attribute(self, name: str, path: str, shape) -> str:
+    def _attribute(self, name: str, path: str, shape, hdf_file: str = None) -> str:
         """One attribute entry, or an empty string if the dataset lives neither on the cells nor on the vertices."""
+        hdf_file = hdf_file or self._hdf_file_name
         if len(shape) == 0:
             return ""
         if shape[0] == self._n_cells:
@@ -354,7 +391,7 @@ class XDMFWriter:
         width = 1 if len(shape) == 1 else shape[1]
         return (f'<Attribute Name="{name}" AttributeType="Vector" Center="{center}">\n'
                 f'<DataItem NumberType="Float" Precision="8" Format="HDF" Dimensions="{n} {width}">\n'
-                f'{self._hdf_file_name}:/{path}\n</DataItem>\n</Attribute>\n')
+                f'{hdf_file}:/{path}\n</DataItem>\n</Attribute>\n')
 
     def _constant_attributes(self) -> str:
         if not self._store.has(CONST):
@@ -362,6 +399,8 @@ class XDMFWriter:
             return ""
         out = []
         for k in self._store.keys(CONST):
+            if k == PART_FILES:
+                continue
             shape = self._store.shape(f"{CONST}/{k}")
             if len(shape) and shape[0] in (self._n_cells, self._n_vertices):
                 out.append(self._attribute(k, f"{CONST}/{k}", shape))
@@ -371,17 +410,18 @@ class XDMFWriter:
     def write_xdmf(self) -> None:
         header = '<?xml version="1.0"?>\n<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>\n<Xdmf Version="2.0">\n'
         parts = [header]
-        if self._store.has(DATA):
+        if self._time_files:
             parts.append(f'<Domain>\n<Grid Name="{self._grid_name}" GridType="Collection" CollectionType="temporal">\n')
-            for i, t in enumerate(sorted(self._store.keys(DATA), key=lambda x: float(x))):
+            for i, t in enumerate(sorted(self._time_files.keys(), key=lambda x: float(x))):
+                hdf_file, st = self._time_files[t]
                 parts.append(f'<Grid Name="{self._grid_name} {t}" GridType="Uniform">\n<Time Value="{t}"/>\n')
                 parts.append(self._topology_and_geometry())
                 if i == 0:
                     parts.append(self._constant_attributes())
-                for k in self._store.keys(f"{DATA}/{t}"):
+                for k in st.keys(f"{DATA}/{t}"):
                     # fields are stored as <field_name>_<position>
                     name = "_".join(k.split("_")[:-1]) if len(k.split("_")) > 1 else k
-                    parts.append(self._attribute(name, f"{DATA}/{t}/{k}", self._store.shape(f"{DATA}/{t}/{k}")))
+                    parts.append(self._attribute(name, f"{DATA}/{t}/{k}", st.shape(f"{DATA}/{t}/{k}"), hdf_file))
                 parts.append('</Grid>\n')
             parts.append('</Grid>\n</Domain>\n</Xdmf>')
         else:

@@ -259,7 +259,7 @@ class ExportData:
     def __init__(self, s_cube, write_new_file_for_each_field: bool = False, n_jobs: int = None,
                  n_neighbors: int = None, interpolate_at_vertices: bool = False, write_times: Union[list, str] = None,
                  append_existing: bool = False, out_dtype=None, device=None, write_files: bool = True,
-                 stream_host: bool = True, async_host: bool = False):
+                 stream_host: bool = True, async_host: bool = False, distributed: bool = False, group=None):
         """
         Arguments up to ``append_existing`` as in the reference (export.py:41-72). Extensions: ``out_dtype``
         (``torch.float64`` = the reference's result dtype), ``device``, ``write_files=False`` (keep the interpolated
@@ -268,6 +268,16 @@ class ExportData:
         gets a fresh pinned result tensor (the reference's semantics: the caller may refill ``data`` and keep results);
         ``async_host=True`` only enqueues and re-uses one pinned result buffer per (field, shape) -- the caller must
         not touch ``data`` or rely on an earlier result before ``synchronize()``.
+
+        ``distributed=True`` (inside an initialised ``torch.distributed`` job, one process per GPU): the export is
+        sharded by snapshot window. Every rank constructs the object with the same grid and calls
+        ``export(coordinates, data_local, field, n_snapshots_total=T)`` with ITS window of the time axis
+        (``parallel.snapshot_window(T, world, rank)``, in one or several batches); ``write_times`` is the full list of
+        all T steps. Rank 0 builds the KNN tables and broadcasts them once (``KnnTables.share``); there is no
+        collective inside the interpolation. Every rank writes its own time steps: rank 0 into ``<save_name>.h5``
+        (with the grid), rank r into ``<save_name>.part<r>.h5``; after the last batch rank 0 records the part list in
+        ``constant/part_files`` and writes ONE XDMF file whose time steps point at the part that holds them.
+        ``Dataloader`` follows the part list, so ``load_snapshot`` returns the complete time series.
         """
         _lib.require_cuda()
         self._device = pt.device(device) if device is not None else pt.device("cuda", pt.cuda.current_device())
@@ -320,6 +330,13 @@ class ExportData:
         self._coord_shape = None
         self._chunk_size = None
         self.metric_on_grid = None
+        self._group = group
+        self._rank, self._world = 0, 1
+        if distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                self._rank, self._world = dist.get_rank(group), dist.get_world_size(group)
+        self._window = None                      # (t0, t1) of this rank in the global time axis
         self._stream_host = stream_host          # host batches: pipelined pitched copies
         self._async_host = async_host
         self._stream_min_elements = 1 << 22
@@ -372,6 +389,16 @@ class ExportData:
             self._interpolated_metric = True
         if self._snapshot_counter == 0:
             self._n_snapshots_total = _n_snapshots_total if _n_snapshots_total is not None else _data.size(-1)
+            if self._world > 1:
+                from .parallel import snapshot_window
+                if _n_snapshots_total is None:
+                    raise ValueError("a distributed export needs ``n_snapshots_total`` (the global number of snapshots)")
+                self._window = snapshot_window(int(_n_snapshots_total), self._world, self._rank)
+            else:
+                self._window = (0, int(self._n_snapshots_total))
+        if self._snapshot_counter + _data.size(-1) > self._window[1] - self._window[0]:
+            raise ValueError(f"rank {self._rank} owns {self._window[1] - self._window[0]} snapshots "
+                             f"[{self._window[0]}, {self._window[1]}) but received {self._snapshot_counter + _data.size(-1)}")
 
         if (not _data.is_cuda and _data.dtype == pt.float32 and self._out_dtype in (None, pt.float32)
                 and self._stream_host and _data.numel() >= self._stream_min_elements):
@@ -452,11 +479,20 @@ class ExportData:
         if self._coord_shape is not None and _coord.shape != self._coord_shape:
             logger.warning("CFD grid change detected. Re-computing interpolation weights of the KNN.")
         self._coord_shape = _coord.shape
+        if self._rank == 0:
+            self._make_tables(_coord)
+        if self._world > 1:                      # one-off broadcast of the tables (NCCL over NVLink)
+            self._tables_centers = KnnTables.share(self._tables_centers, self._device, 0, self._group)
+            if self._interpolate_at_vertices:
+                self._tables_vertices = KnnTables.share(self._tables_vertices, self._device, 0, self._group)
+        self._initialized_weights = True
+
+    def _make_tables(self, _coord: pt.Tensor) -> None:
+        """Device KNN index over the original points and the (idx, w) tables of the sampled grid (rank 0 only)."""
         index = KnnIndex(_coord, device=self._device)
         self._tables_centers = KnnTables(index, self._centers, self._n_neighbors)
         if self._interpolate_at_vertices:
             self._tables_vertices = KnnTables(index, self._vertices, self._n_neighbors)
-        self._initialized_weights = True
         del index
 
     # reference-compatible views of the cache
@@ -468,25 +504,33 @@ class ExportData:
     def _knn_w_centers(self):
         return None if self._tables_centers is None else self._tables_centers.w64
 
+    def _finished_window(self) -> bool:
+        return self._snapshot_counter == self._window[1] - self._window[0]
+
+    def _part_name(self, rank: int) -> str:
+        """File of rank ``rank``: the reference's name for rank 0, ``<name>.part<r>.h5`` otherwise."""
+        stem = f"{self._save_name}_{self._field_name}" if self._new_file else f"{self._save_name}"
+        return f"{stem}.h5" if rank == 0 else f"{stem}.part{rank}.h5"
+
     def _write_data(self) -> None:
         # export.py:233-319
         if not self._write_files:
-            if self._snapshot_counter == self._n_snapshots_total:
+            if self._finished_window():
                 self._interpolated_fields = Fields()
                 self._snapshot_counter = 0
             return
         if not self._initialized_hdf5:
             logger.info(f"Writing HDF5 file for field {self._field_name}.")
             if not path.exists(self._save_dir):
-                makedirs(self._save_dir)
-            name = f"{self._save_name}_{self._field_name}.h5" if self._new_file else f"{self._save_name}.h5"
-            self._datawriter = Datawriter(self._save_dir, name)
-            self._datawriter.write_data(FACES, group=GRID, data=self._face_id)
-            self._datawriter.write_data(VERTICES, group=GRID, data=self._vertices)
-            self._datawriter.write_data(CENTERS, group=GRID, data=self._centers)
-            self._datawriter.write_data("levels", group=CONST, data=self._levels)
-            self._datawriter.write_data("metric", group=CONST, data=self._metric)
-            self._datawriter.write_data("size_initial_cell", group=CONST, data=self._size_initial_cell)
+                makedirs(self._save_dir, exist_ok=True)
+            self._datawriter = Datawriter(self._save_dir, self._part_name(self._rank))
+            if self._rank == 0:
+                self._datawriter.write_data(FACES, group=GRID, data=self._face_id)
+                self._datawriter.write_data(VERTICES, group=GRID, data=self._vertices)
+                self._datawriter.write_data(CENTERS, group=GRID, data=self._centers)
+                self._datawriter.write_data("levels", group=CONST, data=self._levels)
+                self._datawriter.write_data("metric", group=CONST, data=self._metric)
+                self._datawriter.write_data("size_initial_cell", group=CONST, data=self._size_initial_cell)
             self._initialized_hdf5 = True
             if not self._new_file:
                 # one file for all fields: the grid constants are written once and can go. With one file per field the
@@ -497,15 +541,15 @@ class ExportData:
                 self._size_initial_cell = None
         else:
             if not self._new_file and self._datawriter is None:
-                self._datawriter = Datawriter(self._save_dir, f"{self._save_name}.h5", mode="a")
+                self._datawriter = Datawriter(self._save_dir, self._part_name(self._rank), mode="a")
             else:
                 self._datawriter.mode = "a"
 
         self.synchronize()
         centers = self._interpolated_fields.centers.cpu()
         vertices = self._interpolated_fields.vertices.cpu() if self._interpolate_at_vertices else None
-        t_start = self._snapshot_counter - centers.size(-1)
-        t_end = self._snapshot_counter
+        t_end = self._window[0] + self._snapshot_counter          # position in the GLOBAL list of write times
+        t_start = t_end - centers.size(-1)
         for i, t in enumerate(self._write_times[t_start:t_end]):
             if centers.size(1) == 1:
                 self._datawriter.write_data(f"{self._field_name}_center", group=DATA, time_step=str(t),
@@ -519,9 +563,23 @@ class ExportData:
                 if vertices is not None:
                     self._datawriter.write_data(f"{self._field_name}_vertices", group=DATA, time_step=str(t),
                                                 data=vertices[:, :, i])
-        if self._snapshot_counter == self._n_snapshots_total:
-            self._datawriter.close()
-            self._datawriter.write_xdmf_file()
+        if self._finished_window():
+            parts = [self._part_name(r) for r in range(1, self._world)]
+            if self._world > 1:
+                import torch.distributed as dist
+                self._datawriter.close()
+                dist.barrier(group=self._group)                  # every part file is complete and closed
+                if self._rank == 0:
+                    self._datawriter.mode = "a"
+                    self._datawriter.write_part_files(parts)
+            if self._rank == 0:
+                self._datawriter.close()
+                self._datawriter.write_xdmf_file()
+            else:
+                self._datawriter.close()
+            if self._world > 1:
+                import torch.distributed as dist
+                dist.barrier(group=self._group)                  # the XDMF file exists when export() returns anywhere
             self._interpolated_fields = Fields()
             self._snapshot_counter = 0
             if self._new_file:
