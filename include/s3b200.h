@@ -88,20 +88,27 @@ int s3_cells_gain(const s3_knn_t* knn, const double* d_center, const int32_t* d_
  * d_geom_par fp64 flat parameters (layout per type: the classes in sparsespatialsampling_b200/geometry).
  * only_geom >= 0 restricts the test to one geometry; refine_mode = the reference's refine_geometry;
  * apply != 0 additionally marks invalid cells (flags = invalid, gain = 0; s_cube.py:721-731).
- * d_invalid uint8 [n]: 1 where check_cell() returned True for some geometry.                        */
+ * d_invalid uint8 [n]: 1 where check_cell() returned True for some geometry.
+ * Closed triangulated surfaces (GeometrySTL3D, geometry_STL_3d.py:81-124): bit g of `stl_geoms` says that geometry g
+ * is of that type and stored in the tiled layout (triangles in Morton order + one bounding box per 128 triangles, see
+ * csrc/stl.cuh); those are evaluated by a separate kernel -- one thread per node, triangle tiles streamed through
+ * shared memory, tiles and triangles rejected by bounding box -- before the mask kernel combines the flags.
+ * `stl_meta` is a HOST array int32 [n_geoms, 2] = {parameter offset, n_triangles} (the header's numbers);
+ * stl_geoms = 0 keeps every geometry on the per-thread path.                                          */
 int s3_cells_mask(const double* d_center, const int32_t* d_level, const int64_t* d_cells, int64_t first,
                   int64_t n, int dim, double width, const int32_t* d_geom_hdr, const double* d_geom_par,
                   int n_geoms, int only_geom, int refine_mode, int apply, uint8_t* d_invalid,
-                  uint8_t* d_flags, double* d_gain, void* stream);
+                  uint8_t* d_flags, double* d_gain, int stl_geoms, const int32_t* stl_meta, void* stream);
 
 /* GeometryObject.check_cell on explicit node sets: d_nodes fp64 [n, n_nodes, dim] -> d_invalid uint8 [n]
  * (geometry/geometry_base.py:150-163 and the per-shape check_cell methods)                           */
 int s3_nodes_mask(const double* d_nodes, int64_t n, int n_nodes, int dim, const int32_t* d_geom_hdr,
                   const double* d_geom_par, int n_geoms, int only_geom, int refine_mode,
-                  uint8_t* d_invalid, void* stream);
+                  uint8_t* d_invalid, int stl_geoms, const int32_t* stl_meta, void* stream);
 /* per-point inside mask of geometry `geom` (the reference's _mask_* / check_triangle / check_tetrahedron) */
 int s3_points_inside(const double* d_points, int64_t n, int dim, const int32_t* d_geom_hdr,
-                     const double* d_geom_par, int geom, uint8_t* d_inside, void* stream);
+                     const double* d_geom_par, int geom, uint8_t* d_inside, int stl_geoms, const int32_t* stl_meta,
+                     void* stream);
 
 /* heapq.nlargest(k, leaf, key=(gain, -idx)) (s_cube.py:601-602): radix select + stable radix sort.
  * d_out int64 [k], ordered by (gain descending, index ascending). Requires k <= number of leaves.   */

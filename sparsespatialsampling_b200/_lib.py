@@ -41,10 +41,11 @@ _SIGNATURES = {
     "s3_cells_gain": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_double, c_double, c_int,
                               c_void_p, c_void_p, c_void_p]),
     "s3_cells_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p, c_int,
-                              c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "s3_nodes_mask": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                              c_void_p]),
-    "s3_points_inside": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                              c_int, c_void_p, c_void_p]),
+    "s3_points_inside": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                 c_void_p]),
     "s3_select_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "s3_select_set_fused": (c_int, [c_int]),
     "s3_build_nodes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p,

@@ -5,6 +5,7 @@
 //   cell's own level), gain fp64 [cap], metric fp64 [cap], flags uint8 [cap].
 #include "common.cuh"
 #include "geometry.cuh"
+#include "stl.cuh"
 #include "knn.cuh"
 #include "radix_sort.cuh"
 #include "../../include/s3b200.h"
@@ -108,12 +109,25 @@ cells_gain_kernel(KnnView ix, const double* __restrict__ center, const int32_t* 
 }
 
 // ---------------------------------------------------------------- geometry mask (s_cube.py:669-732, :1816-1837)
+// STL geometries evaluated beforehand by stl_inside_kernel (one flag per node): slot i holds geometry geom[i]
+constexpr int kMaxStlPre = 4;
+struct StlPre {
+    const uint8_t* inside[kMaxStlPre];
+    int geom[kMaxStlPre];
+    int n;
+};
+__device__ __forceinline__ const uint8_t* stl_pre_of(const StlPre& pre, int g) {
+    for (int i = 0; i < pre.n; ++i)
+        if (pre.geom[i] == g) return pre.inside[i];
+    return nullptr;
+}
+
 __global__ void __launch_bounds__(128)
 cells_mask_kernel(const double* __restrict__ center, const int32_t* __restrict__ level,
                   const int64_t* __restrict__ cells, int64_t first, int64_t n, int dim, double width,
                   const int32_t* __restrict__ geom_hdr, const double* __restrict__ geom_par, int n_geoms,
                   int only_geom, int refine_mode, int apply, uint8_t* __restrict__ out_invalid,
-                  uint8_t* __restrict__ flags, double* __restrict__ gain) {
+                  uint8_t* __restrict__ flags, double* __restrict__ gain, const StlPre pre) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int64_t cell = cells ? cells[t] : first + t;
@@ -135,7 +149,12 @@ cells_mask_kernel(const double* __restrict__ center, const int32_t* __restrict__
         hd.n_extra = geom_hdr[4 * g + 3];
         if (hd.type == GEOM_CUSTOM) continue;
         int n_in = 0;
-        for (int j = 0; j < nn; ++j) n_in += point_in_geometry(hd, geom_par + hd.offset, node[j], dim) ? 1 : 0;
+        const uint8_t* staged = hd.type == GEOM_STL ? stl_pre_of(pre, g) : nullptr;
+        if (staged) {
+            for (int j = 0; j < nn; ++j) n_in += staged[t * nn + j];
+        } else {
+            for (int j = 0; j < nn; ++j) n_in += point_in_geometry(hd, geom_par + hd.offset, node[j], dim) ? 1 : 0;
+        }
         invalid = apply_mask(n_in, nn, hd.keep_inside != 0, refine_mode != 0);
     }
     out_invalid[t] = invalid ? 1 : 0;
@@ -150,7 +169,7 @@ cells_mask_kernel(const double* __restrict__ center, const int32_t* __restrict__
 __global__ void __launch_bounds__(128)
 nodes_mask_kernel(const double* __restrict__ nodes, int64_t n, int nn, int dim, const int32_t* __restrict__ geom_hdr,
                   const double* __restrict__ geom_par, int n_geoms, int only_geom, int refine_mode,
-                  uint8_t* __restrict__ out_invalid) {
+                  uint8_t* __restrict__ out_invalid, const StlPre pre) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     bool invalid = false;
@@ -163,7 +182,9 @@ nodes_mask_kernel(const double* __restrict__ nodes, int64_t n, int nn, int dim, 
         hd.n_extra = geom_hdr[4 * g + 3];
         if (hd.type == GEOM_CUSTOM) continue;
         int n_in = 0;
+        const uint8_t* staged = hd.type == GEOM_STL ? stl_pre_of(pre, g) : nullptr;
         for (int j = 0; j < nn; ++j) {
+            if (staged) { n_in += staged[t * nn + j]; continue; }
             double p[3] = {0, 0, 0};
             for (int a = 0; a < dim; ++a) p[a] = nodes[(t * nn + j) * dim + a];
             n_in += point_in_geometry(hd, geom_par + hd.offset, p, dim) ? 1 : 0;
@@ -622,17 +643,51 @@ int s3_cells_gain(const s3_knn_t* knn, const double* d_center, const int32_t* d_
     return S3_OK;
 }
 
+// Pre-pass of the mask entry points: the geometries named by the bit mask `stl_geoms` are closed triangulated surfaces
+// (GEOM_STL); their per-node inside flags are computed by the tiled kernel of stl.cuh into stream-ordered scratch.
+// n_tri of each geometry is read from the (host-visible copy of the) header the caller passes in `stl_ntri`.
+static int stl_prepass(Scratch& scratch, const StlPoints& src, int64_t n_pts, const int32_t* d_geom_hdr,
+                       const double* d_geom_par, int n_geoms, int only_geom, int stl_geoms, const int32_t* stl_meta,
+                       StlPre* pre, cudaStream_t st) {
+    pre->n = 0;
+    for (int g = 0; g < n_geoms && g < 31; ++g) {
+        if (!((stl_geoms >> g) & 1) || (only_geom >= 0 && g != only_geom)) continue;
+        if (pre->n == kMaxStlPre) break;                                 // further STL surfaces take the per-thread path
+        uint8_t* flags = nullptr;
+        S3_TRY(scratch.alloc(&flags, (size_t)n_pts));
+        // stl_meta (host): {parameter offset, n_tri} per geometry, the same numbers as in the device header
+        const int offset = stl_meta[2 * g], n_tri = stl_meta[2 * g + 1];
+        stl_inside_kernel<<<(unsigned)ceil_div(n_pts, kStlThreads), kStlThreads, 0, st>>>(src, n_pts, d_geom_par + offset,
+                                                                                        n_tri, flags);
+        S3_LAUNCH_CHECK();
+        note_launch(1);
+        pre->inside[pre->n] = flags;
+        pre->geom[pre->n] = g;
+        ++pre->n;
+    }
+    return S3_OK;
+}
+
 int s3_cells_mask(const double* d_center, const int32_t* d_level, const int64_t* d_cells, int64_t first, int64_t n,
                   int dim, double width, const int32_t* d_geom_hdr, const double* d_geom_par, int n_geoms,
                   int only_geom, int refine_mode, int apply, uint8_t* d_invalid, uint8_t* d_flags, double* d_gain,
-                  void* stream) {
+                  int stl_geoms, const int32_t* stl_meta, void* stream) {
     S3_REQUIRE(d_center && d_level && d_invalid, "s3_cells_mask: NULL argument");
     S3_REQUIRE(n_geoms == 0 || (d_geom_hdr && d_geom_par), "s3_cells_mask: geometry tables missing");
     S3_REQUIRE(!apply || (d_flags && d_gain), "s3_cells_mask: apply needs flags and gain");
+    S3_REQUIRE(stl_geoms == 0 || stl_meta, "s3_cells_mask: stl_geoms needs stl_meta");
     if (n == 0) return S3_OK;
-    cells_mask_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch scratch(st);
+    StlPre pre{};
+    if (stl_geoms && dim == 3) {
+        StlPoints src{};
+        src.mode = 0; src.center = d_center; src.level = d_level; src.cells = d_cells; src.first = first; src.width = width;
+        S3_TRY(stl_prepass(scratch, src, n * 8, d_geom_hdr, d_geom_par, n_geoms, only_geom, stl_geoms, stl_meta, &pre, st));
+    }
+    cells_mask_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(
         d_center, d_level, d_cells, first, n, dim, width, d_geom_hdr, d_geom_par, n_geoms, only_geom, refine_mode,
-        apply, d_invalid, d_flags, d_gain);
+        apply, d_invalid, d_flags, d_gain, pre);
     S3_LAUNCH_CHECK();
     note_launch(1);
     return S3_OK;
@@ -640,25 +695,45 @@ int s3_cells_mask(const double* d_center, const int32_t* d_level, const int64_t*
 
 int s3_nodes_mask(const double* d_nodes, int64_t n, int n_nodes, int dim, const int32_t* d_geom_hdr,
                   const double* d_geom_par, int n_geoms, int only_geom, int refine_mode, uint8_t* d_invalid,
-                  void* stream) {
+                  int stl_geoms, const int32_t* stl_meta, void* stream) {
     S3_REQUIRE(d_nodes && d_invalid && d_geom_hdr && d_geom_par, "s3_nodes_mask: NULL argument");
     S3_REQUIRE(dim == 2 || dim == 3, "s3_nodes_mask: dim must be 2 or 3");
     S3_REQUIRE(n_nodes >= 1 && n_nodes <= 64, "s3_nodes_mask: n_nodes out of range");
+    S3_REQUIRE(stl_geoms == 0 || stl_meta, "s3_nodes_mask: stl_geoms needs stl_meta");
     if (n == 0) return S3_OK;
-    nodes_mask_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
-        d_nodes, n, n_nodes, dim, d_geom_hdr, d_geom_par, n_geoms, only_geom, refine_mode, d_invalid);
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch scratch(st);
+    StlPre pre{};
+    if (stl_geoms && dim == 3) {
+        StlPoints src{};
+        src.mode = 1; src.points = d_nodes;
+        S3_TRY(stl_prepass(scratch, src, n * n_nodes, d_geom_hdr, d_geom_par, n_geoms, only_geom, stl_geoms, stl_meta, &pre, st));
+    }
+    nodes_mask_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(
+        d_nodes, n, n_nodes, dim, d_geom_hdr, d_geom_par, n_geoms, only_geom, refine_mode, d_invalid, pre);
     S3_LAUNCH_CHECK();
     note_launch(1);
     return S3_OK;
 }
 
 int s3_points_inside(const double* d_points, int64_t n, int dim, const int32_t* d_geom_hdr, const double* d_geom_par,
-                     int geom, uint8_t* d_inside, void* stream) {
+                     int geom, uint8_t* d_inside, int stl_geoms, const int32_t* stl_meta, void* stream) {
     S3_REQUIRE(d_points && d_inside && d_geom_hdr && d_geom_par, "s3_points_inside: NULL argument");
     S3_REQUIRE(dim == 2 || dim == 3, "s3_points_inside: dim must be 2 or 3");
+    S3_REQUIRE(stl_geoms == 0 || stl_meta, "s3_points_inside: stl_geoms needs stl_meta");
     if (n == 0) return S3_OK;
-    points_inside_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_points, n, dim, d_geom_hdr,
-                                                                                     d_geom_par, geom, d_inside);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dim == 3 && geom >= 0 && geom < 31 && ((stl_geoms >> geom) & 1)) {
+        StlPoints src{};
+        src.mode = 1; src.points = d_points;
+        stl_inside_kernel<<<(unsigned)ceil_div(n, kStlThreads), kStlThreads, 0, st>>>(
+            src, n, d_geom_par + stl_meta[2 * geom], stl_meta[2 * geom + 1], d_inside);
+        S3_LAUNCH_CHECK();
+        note_launch(1);
+        return S3_OK;
+    }
+    points_inside_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(d_points, n, dim, d_geom_hdr, d_geom_par, geom,
+                                                                    d_inside);
     S3_LAUNCH_CHECK();
     note_launch(1);
     return S3_OK;

@@ -217,40 +217,49 @@ class KnnTables:
         return self
 
     @classmethod
-    def share(cls, tables: "KnnTables", device, src: int = 0, group=None) -> "KnnTables":
+    def share(cls, tables: "KnnTables", device, src: int = 0, group=None, n: int = None, k: int = None) -> "KnnTables":
         """
         Sharded export: rank ``src`` passes the tables it built, every other rank passes ``None`` and
-        receives a copy -- one header + six tensor broadcasts (NCCL over NVLink; gloo moves them through the host).
-        This is the only collective of the export stage; the interpolation itself has none.
+        receives a copy. ONE broadcast of one packed buffer (Morton-ordered indices, fp64 weights, output rows: 100 bytes
+        per cell for k = 8; NCCL over NVLink, gloo moves it through the host) -- the fp32 weights and the views in the
+        reference's cell order are derived locally. ``n`` / ``k`` (cells, neighbours), when the receivers know them,
+        save the header broadcast and its host synchronisation. This is the only collective of the export stage.
         """
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return tables
         dev = pt.device(device)
         on_host = dist.get_backend(group) == "gloo"
+        wire = pt.device("cpu") if on_host else dev
         root = dist.get_global_rank(group, src) if group is not None else src
-        head = pt.zeros(2, dtype=pt.int64, device="cpu" if on_host else dev)
-        if dist.get_rank(group) == src:
-            head[0], head[1] = tables.n, tables.k
-        dist.broadcast(head, src=root, group=group)
-        n, k = int(head[0]), int(head[1])
-        if dist.get_rank(group) != src:
+        is_src = dist.get_rank(group) == src
+        if n is None or k is None:
+            head = pt.zeros(2, dtype=pt.int64, device=wire)
+            if is_src:
+                head[0], head[1] = tables.n, tables.k
+            dist.broadcast(head, src=root, group=group)
+            n, k = int(head[0]), int(head[1])
+        words = n * k + n + 2 * n * k                      # int32 words: idx | out_row | fp64 weights
+        if is_src:
+            assert tables.n == n and tables.k == k
+            buf = pt.cat([tables.idx_sorted.reshape(-1), tables.out_row.reshape(-1),
+                          tables.w64_sorted.reshape(-1).view(pt.int32)]).to(wire)
+        else:
+            buf = pt.empty(words, dtype=pt.int32, device=wire)
+        dist.broadcast(buf, src=root, group=group)
+        if not is_src:
+            buf = buf.to(dev)
             tables = cls.__new__(cls)
             tables.n, tables.k, tables._inflight = n, k, []
-            tables.idx = pt.empty((n, k), dtype=pt.int32, device=dev)
-            tables.w64 = pt.empty((n, k), dtype=pt.float64, device=dev)
-            tables.idx_sorted = pt.empty((n, k), dtype=pt.int32, device=dev)
-            tables.w32_sorted = pt.empty((n, k), dtype=pt.float32, device=dev)
-            tables.w64_sorted = pt.empty((n, k), dtype=pt.float64, device=dev)
-            tables.out_row = pt.empty((n,), dtype=pt.int32, device=dev)
-        for name in ("idx", "w64", "idx_sorted", "w32_sorted", "w64_sorted", "out_row"):
-            t = getattr(tables, name)
-            if on_host:
-                h = t.cpu()
-                dist.broadcast(h, src=root, group=group)
-                t.copy_(h)
-            else:
-                dist.broadcast(t, src=root, group=group)
+            tables.idx_sorted = buf[:n * k].reshape(n, k).contiguous()
+            tables.out_row = buf[n * k:n * k + n].contiguous()
+            tables.w64_sorted = buf[n * k + n:].clone().view(pt.float64).reshape(n, k)
+            tables.w32_sorted = tables.w64_sorted.to(pt.float32)          # the kernel's own rule: (float) of the fp64 weight
+            rows = tables.out_row.long()
+            tables.idx = pt.empty_like(tables.idx_sorted)
+            tables.idx[rows] = tables.idx_sorted                          # views in the reference's cell order
+            tables.w64 = pt.empty_like(tables.w64_sorted)
+            tables.w64[rows] = tables.w64_sorted
         tables._rows_unique = None
         return tables
 
@@ -482,9 +491,11 @@ class ExportData:
         if self._rank == 0:
             self._make_tables(_coord)
         if self._world > 1:                      # one-off broadcast of the tables (NCCL over NVLink)
-            self._tables_centers = KnnTables.share(self._tables_centers, self._device, 0, self._group)
+            self._tables_centers = KnnTables.share(self._tables_centers, self._device, 0, self._group,
+                                                   n=self._centers.size(0), k=self._n_neighbors)
             if self._interpolate_at_vertices:
-                self._tables_vertices = KnnTables.share(self._tables_vertices, self._device, 0, self._group)
+                self._tables_vertices = KnnTables.share(self._tables_vertices, self._device, 0, self._group,
+                                                        n=self._vertices.size(0), k=self._n_neighbors)
         self._initialized_weights = True
 
     def _make_tables(self, _coord: pt.Tensor) -> None:

@@ -7,8 +7,14 @@ one flat fp64 parameter array.
 """
 import torch as pt
 
+import ctypes
+
+import numpy as np
+
 from .. import _lib
 from .base import GEOM_CUSTOM
+
+GEOM_STL = 7
 
 
 class GeometryTable:
@@ -29,6 +35,18 @@ class GeometryTable:
         self.n = len(geometries)
         self.hdr = pt.tensor(hdr, dtype=pt.int32, device=device).contiguous()
         self.par = pt.tensor(par, dtype=pt.float64, device=device).contiguous()
+        # closed triangulated surfaces take the tiled kernel (csrc/stl.cuh): bit mask of their positions and a HOST
+        # copy of {parameter offset, n_triangles} per geometry for the launcher
+        self.stl_geoms = 0
+        for i, h in enumerate(hdr):
+            if h[0] == GEOM_STL and i < 31:
+                self.stl_geoms |= 1 << i
+        self._stl_meta = np.ascontiguousarray([[h[2], h[3]] for h in hdr], dtype=np.int32)
+
+    @property
+    def stl_meta(self):
+        """Host pointer of the int32 [n, 2] table {parameter offset, n_triangles} (NULL without STL geometries)."""
+        return self._stl_meta.ctypes.data_as(ctypes.c_void_p) if self.stl_geoms else None
 
 
 def nodes_invalid(geometries: list, nodes: pt.Tensor, refine_geometry: bool = False, only_geom: int = -1) -> pt.Tensor:
@@ -44,7 +62,8 @@ def nodes_invalid(geometries: list, nodes: pt.Tensor, refine_geometry: bool = Fa
     n, nn, dim = nd.shape
     out = pt.empty((n,), dtype=pt.uint8, device=dev)
     _lib.check(lib.s3_nodes_mask(_lib.ptr(nd), n, nn, dim, _lib.ptr(table.hdr), _lib.ptr(table.par), table.n,
-                                 only_geom, int(bool(refine_geometry)), _lib.ptr(out), _lib.stream_ptr()))
+                                 only_geom, int(bool(refine_geometry)), _lib.ptr(out), table.stl_geoms, table.stl_meta,
+                                 _lib.stream_ptr()))
     return out.bool().cpu()
 
 
@@ -57,5 +76,5 @@ def nodes_inside(geometry, points: pt.Tensor) -> pt.Tensor:
     p = points.detach().to(device=dev, dtype=pt.float64).contiguous()
     out = pt.empty((p.size(0),), dtype=pt.uint8, device=dev)
     _lib.check(lib.s3_points_inside(_lib.ptr(p), p.size(0), p.size(1), _lib.ptr(table.hdr), _lib.ptr(table.par), 0,
-                                    _lib.ptr(out), _lib.stream_ptr()))
+                                    _lib.ptr(out), table.stl_geoms, table.stl_meta, _lib.stream_ptr()))
     return out.bool().cpu()

@@ -357,7 +357,8 @@ class SamplingTree(object):
             _lib.check(self._lib.s3_cells_mask(_lib.ptr(self._center), _lib.ptr(self._level), _lib.ptr(cells_d), first, n,
                                                self._n_dimensions, self._width, _lib.ptr(tab.hdr), _lib.ptr(tab.par),
                                                tab.n, only, int(refine_geometry), apply, _lib.ptr(out),
-                                               _lib.ptr(self._flags), _lib.ptr(self._gain), self._stream()))
+                                               _lib.ptr(self._flags), _lib.ptr(self._gain), tab.stl_geoms, tab.stl_meta,
+                                               self._stream()))
         res = out[:n].cpu().numpy().astype(bool)
         if tab.custom:
             res = self._mask_custom(cells, res, refine_geometry, only, apply)

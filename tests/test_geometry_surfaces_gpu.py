@@ -133,3 +133,99 @@ def test_grid_generation_with_stl_and_polygon_matches_oracle(cuda, tmp_path):
     assert list(t2._leaf_cells) == o2.leaf_order
     assert np.array_equal(t2.all_centers.numpy(), o2.all_centers)
     assert np.array_equal(t2.all_levels.numpy(), o2.all_levels)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Closed-form solids. The STL rule restated from geometry_STL_3d.py:81-103 / vtkSelectEnclosedPoints:
+# a point within tol = 0.001 * bounding-box diagonal of the surface counts as inside, everything else by ray parity.
+# The pins below only assert points that are farther than tol + the faceting error from the analytic surface, where
+# inside / outside does not depend on that band rule; inside the band the device is compared with the oracle only.
+def _solids(tmp_path):
+    from tests.stl_util import torus_triangles, l_extrusion_triangles, in_l_extrusion
+    rng = np.random.default_rng(0)
+    out = []
+    # sphere r = 0.7 around c: icosphere with 5120 faces, inscribed -> faceting error r * (1 - cos(half edge angle))
+    c, r = np.array([0.1, -0.2, 0.3]), 0.7
+    tri = icosphere_triangles(4, radius=r, center=c)
+    pts = c + (rng.random((60000, 3)) - 0.5) * 2.2 * r
+    d = np.linalg.norm(pts - c, axis=1) - r
+    facet = 0.004 * r
+    out.append(("sphere", tri, pts, np.where(d < -facet, 1, np.where(d > 0, -1, 0)), d))
+    # torus R = 1, r = 0.35 (48 x 24 quads): distance to the analytic torus
+    tri = torus_triangles(96, 48, 1.0, 0.35)
+    pts = (rng.random((60000, 3)) - 0.5) * np.array([3.0, 3.0, 1.0])
+    d = np.sqrt((np.sqrt(pts[:, 0] ** 2 + pts[:, 1] ** 2) - 1.0) ** 2 + pts[:, 2] ** 2) - 0.35
+    facet = 0.003
+    out.append(("torus", tri, pts, np.where(d < -facet, 1, np.where(d > 0, -1, 0)), d))
+    # L-shaped extrusion: exact planar faces, no faceting error; includes lattice-aligned points
+    tri = l_extrusion_triangles(0.5)
+    pts = np.concatenate([(rng.random((40000, 3)) - 0.25) * np.array([3.0, 3.0, 1.0]),
+                          np.stack(np.meshgrid(np.linspace(-0.5, 2.5, 25), np.linspace(-0.5, 2.5, 25),
+                                               np.linspace(-0.25, 0.75, 9), indexing="ij"), -1).reshape(-1, 3)])
+    out.append(("L", tri, pts, None, None))
+    return out
+
+
+def test_stl_closed_form_solids_pins(cuda, tmp_path):
+    from sparsespatialsampling_b200.geometry import GeometrySTL3D
+    from sparsespatialsampling_b200.geometry.device import nodes_inside
+    from tests.stl_util import in_l_extrusion
+    for name, tri, pts, want, dist in _solids(tmp_path):
+        p = tmp_path / f"{name}.stl"
+        write_binary_stl(p, tri)
+        g = GeometrySTL3D(name, False, str(p))
+        tol = g._tolerance
+        got = nodes_inside(g, pt.from_numpy(pts)).numpy()
+        # device == CPU oracle on every point, including the tolerance band
+        assert np.array_equal(got, orc.points_inside(g, pts)), name
+        if name == "L":
+            cls = in_l_extrusion(pts, 0.5, margin=tol * 1.001 + 1e-6)    # fp32 STL coordinates: 1e-6 slack
+        else:
+            cls = np.where(want == 1, np.where(dist < -tol - 0.01, 1, 0), np.where(dist > tol, -1, 0))
+        assert (got[cls == 1]).all() and (~got[cls == -1]).all(), name
+        assert (cls == 1).sum() > 2000 and (cls == -1).sum() > 2000
+        # band rule: on the exact planar faces of the L, points within tol of a face (outside) count as inside
+        if name == "L":
+            band = np.stack([np.full(50, 2.0 + 0.5 * tol), np.linspace(0.1, 0.9, 50), np.full(50, 0.25)], 1)
+            far = band + np.array([1.0 * tol, 0, 0])
+            assert nodes_inside(g, pt.from_numpy(band)).numpy().all()
+            assert not nodes_inside(g, pt.from_numpy(far)).numpy().any()
+
+
+@pytest.mark.parametrize("n_sub,n_cells", [(3, 3000), (5, 20000)])
+def test_stl_tiled_kernel_equals_per_thread_path(cuda, tmp_path, n_sub, n_cells):
+    """csrc/stl.cuh (node per thread, triangle tiles through shared memory, box rejects) against the single-point test
+    in_stl evaluated per cell thread (stl_geoms = 0): same flags for cells, explicit nodes and points, all modes."""
+    import ctypes
+    from sparsespatialsampling_b200 import _lib
+    from sparsespatialsampling_b200.geometry import GeometrySTL3D, CubeGeometry
+    from sparsespatialsampling_b200.geometry.device import GeometryTable
+    p = tmp_path / "s.stl"
+    write_binary_stl(p, icosphere_triangles(n_sub, radius=0.31, center=(0.5, 0.45, 0.55)))
+    geoms = [CubeGeometry("domain", True, [0, 0, 0], [1, 1, 1]), GeometrySTL3D("body", False, str(p))]
+    dev = pt.device("cuda")
+    tab = GeometryTable(geoms, dev)
+    assert tab.stl_geoms == 2
+    lib = _lib.load()
+    rng = np.random.default_rng(n_sub)
+    level = pt.from_numpy(rng.integers(3, 7, n_cells).astype(np.int32)).to(dev)
+    center = pt.from_numpy(rng.random((n_cells, 3))).to(dev)
+    for refine_mode in (0, 1):
+        outs = []
+        for stl_geoms, meta in ((tab.stl_geoms, tab.stl_meta), (0, None)):
+            inv = pt.empty(n_cells, dtype=pt.uint8, device=dev)
+            _lib.check(lib.s3_cells_mask(_lib.ptr(center), _lib.ptr(level), None, 0, n_cells, 3, 1.0, _lib.ptr(tab.hdr),
+                                         _lib.ptr(tab.par), tab.n, -1, refine_mode, 0, _lib.ptr(inv), None, None,
+                                         stl_geoms, meta, _lib.stream_ptr()))
+            outs.append(inv.cpu())
+        assert pt.equal(outs[0], outs[1]) and 0 < int(outs[0].sum()) < n_cells
+    pts = pt.from_numpy(rng.random((50000, 3))).to(dev)
+    flags = []
+    for stl_geoms, meta in ((tab.stl_geoms, tab.stl_meta), (0, None)):
+        ins = pt.empty(pts.size(0), dtype=pt.uint8, device=dev)
+        _lib.check(lib.s3_points_inside(_lib.ptr(pts), pts.size(0), 3, _lib.ptr(tab.hdr), _lib.ptr(tab.par), 1,
+                                        _lib.ptr(ins), stl_geoms, meta, _lib.stream_ptr()))
+        flags.append(ins.cpu())
+    assert pt.equal(flags[0], flags[1])
+    vol = float(flags[0].float().mean())
+    assert abs(vol - 4.0 / 3.0 * np.pi * 0.31 ** 3) < 0.01                   # Monte-Carlo volume of the sphere
