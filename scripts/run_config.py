@@ -40,7 +40,7 @@ def fill_field(out: pt.Tensor, coords: pt.Tensor, n_total: int, comps: int, xc: 
     return out
 
 
-def config(name: str, n_cells_max):
+def config(name: str, n_cells_max, stl_subdiv: int = 4):
     geo = s3.geometry
     if name == "C3":
         x = synth.airfoil2d_cloud(synth.CONFIGS["C3"][0], seed=0)
@@ -59,7 +59,7 @@ def config(name: str, n_cells_max):
         x = synth.cylinder3d_cloud(synth.CONFIGS["C5"][0], seed=0)
         zmax = synth.CYL3D["upper"][2]
         stl = "/tmp/s3b200_c5_body.stl"
-        write_binary_stl(stl, icosphere_triangles(4, 0.12, (0.8, 1.0, zmax / 2)))
+        write_binary_stl(stl, icosphere_triangles(stl_subdiv, 0.12, (0.8, 1.0, zmax / 2)))
         geoms = [geo.CubeGeometry("domain", True, synth.CYL3D["lower"], synth.CYL3D["upper"]),
                  geo.GeometrySTL3D("body", False, stl, refine=True)]
         return x, geoms, dict(xc=0.8, yc=1.0), dict(uniform_levels=5, n_cells_max=n_cells_max or 500000)
@@ -77,6 +77,8 @@ def main():
     ap.add_argument("--tune", default="", help="comma separated key=value pairs for s3x_tune (csrc/interp.cu), e.g. 2=1,3=0")
     ap.add_argument("--dense", action="store_true", help="the reference's dense [N, D, T] layout instead of 128-byte pitched rows")
     ap.add_argument("--lattice-vertices", action="store_true", help="exact_topology=False")
+    ap.add_argument("--stl-subdiv", type=int, default=4, help="C5: icosphere subdivisions of the STL body (4: 5120 triangles, 6: 81920)")
+    ap.add_argument("--grid-only", action="store_true", help="stop after grid generation (timings only)")
     ap.add_argument("--e2e", action="store_true", help="also time the host-to-host export (256 snapshots): DMA vs row gather")
     args = ap.parse_args()
     dev = pt.device("cuda", 0)
@@ -86,7 +88,7 @@ def main():
         for kv in args.tune.split(","):
             key, val = kv.split("=")
             _lib.tune(int(key), int(val))
-    x, geoms, wake, grid_kw = config(args.name, args.n_cells_max)
+    x, geoms, wake, grid_kw = config(args.name, args.n_cells_max, args.stl_subdiv)
     d = x.size(1)
     k = 8 if d == 2 else 26
     T = args.snapshots or synth.CONFIGS[args.name][1]
@@ -102,6 +104,13 @@ def main():
     info = sc.mesh_info
     nc = sc.centers.size(0)
     width = sc.size_initial_cell
+    if args.grid_only:
+        print(json.dumps({"config": args.name, "stl_triangles": 20 * 4 ** args.stl_subdiv if args.name == "C5" else None,
+                          "n_points": int(x.size(0)), "n_cells": int(nc), "grid_gen_s": info["t_total"],
+                          "t_uniform": info["t_uniform"], "t_adaptive": info["t_adaptive"], "t_geometry": info["t_geometry"],
+                          "t_renumbering": info["t_renumbering"], "t_knn_build_gridgen": info["t_knn_build"],
+                          "iterations": info["iterations"], "levels": [info["min_level"], info["max_level"]]}))
+        return
 
     # grid consistency
     lv = sc.levels.squeeze(1).numpy()

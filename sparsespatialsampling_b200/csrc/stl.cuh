@@ -9,7 +9,8 @@
 //      extent contains the node and whose x extent reaches beyond it, the tolerance band only triangles whose box
 //      (grown by the tolerance) contains it,
 //   3. streams those tiles through shared memory (cp.async, two stages), computes the per-triangle boxes once per tile,
-//      and every thread tests its node against the staged triangles: box rejects first, then exactly the arithmetic of
+//      and every thread tests its node against the staged triangles: the tile's box, then the triangle's box, then
+//      exactly the arithmetic of
 //      the single-point test in geometry.cuh (in_stl: closest-point distance for the tolerance band, 2-D edge functions
 //      and the x of the hit for the ray) -- the result is the same predicate, order independent (a crossing COUNT and
 //      an OR), hence bit-identical to in_stl and to the CPU oracle.
@@ -158,7 +159,12 @@ stl_inside_kernel(const StlPoints src, int64_t n_pts, const double* __restrict__
                 }
             }
             __syncthreads();
-            if (active) {
+            // this node against the tile's own box first: most (node, tile) pairs of a CTA end here
+            const double* gb = tile_box + (size_t)t * 6;
+            const bool tile_yz = py >= gb[1] && py <= gb[4] && pz >= gb[2] && pz <= gb[5] && gb[3] > p[0];
+            const bool tile_band = p[0] >= gb[0] - tol && p[0] <= gb[3] + tol && p[1] >= gb[1] - tol &&
+                                   p[1] <= gb[4] + tol && p[2] >= gb[2] - tol && p[2] <= gb[5] + tol;
+            if (active && (tile_yz || (tile_band && !near))) {
                 for (int k = 0; k < nt; ++k) {
                     const double* tb = s_tbox[k];
                     const bool in_yz = py >= tb[1] && py <= tb[4] && pz >= tb[2] && pz <= tb[5];
