@@ -446,9 +446,8 @@ def run_ours(args):
             exp.export(x, u_h, "U", n_snapshots_total=N_SNAP)
             r_u = exp.interpolated_fields.centers          # waits for all result copies
             return r_p, r_u
-        e2e_step()
-        e2e_step()                   # the pinned result pool reaches its steady size (two buffers per field) here
-        res_p, res_u = e2e_step()
+        for _ in range(3):           # the pinned result pool reaches its steady size (two buffers per field) here:
+            res_p, res_u = e2e_step()    # the caller still holds the previous step's results when the next one starts
         assert not res_p.is_cuda and not res_u.is_cuda
         assert pt.equal(res_p, check_p.cpu()) and pt.equal(res_u, check_u.cpu()), "streamed export differs from the resident path"
         n = max(2, min(args.steps, 8))

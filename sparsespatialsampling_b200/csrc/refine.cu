@@ -423,6 +423,14 @@ __device__ __forceinline__ bool key96_prefix_equal(const Key96& a, const Key96& 
     }
     return a.hi == b.hi && (shift >= 32 ? true : ((a.lo >> shift) == (b.lo >> shift)));
 }
+// is the part of a above bit `shift` >= the same part of b?
+__device__ __forceinline__ bool key96_top_ge(const Key96& a, const Key96& b, int shift) {
+    if (shift >= 32) {
+        const int s = shift - 32;
+        return (a.hi >> s) >= (b.hi >> s);
+    }
+    return a.hi > b.hi || (a.hi == b.hi && (a.lo >> shift) >= (b.lo >> shift));
+}
 __device__ __forceinline__ bool key96_ge(const Key96& a, const Key96& b) {
     return a.hi > b.hi || (a.hi == b.hi && a.lo >= b.lo);
 }
@@ -446,10 +454,12 @@ __device__ __forceinline__ void fused_grid_barrier(uint32_t* counter, uint32_t& 
 __global__ void __launch_bounds__(kFusedThreads, 1)
 select_fused_kernel(const double* __restrict__ gain, const uint8_t* __restrict__ flags, int64_t n, uint32_t k,
                     FusedSelectState* st, uint64_t* __restrict__ win_key, uint32_t* __restrict__ win_idx,
-                    int64_t* __restrict__ out, int sort_in_kernel) {
+                    int64_t* __restrict__ out, int sort_in_kernel, uint32_t max_candidates) {
     extern __shared__ __align__(16) unsigned char fused_smem[];
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(fused_smem);            // [kFusedBins], re-used by the sort
-    __shared__ uint32_t s_digit, s_rem;
+    __shared__ uint32_t s_digit, s_rem, s_cnt;
+    int final_shift = 0;
+    uint32_t n_cand = k;
     uint32_t generation = 0;
     Key96 prefix{0ull, 0u};
     uint32_t remaining = k;
@@ -495,37 +505,46 @@ select_fused_kernel(const double* __restrict__ gain, const uint8_t* __restrict__
                 }
                 s_digit = (uint32_t)digit;
                 s_rem = rem;
+                s_cnt = h[digit];
             }
         }
         __syncthreads();
         const uint32_t digit = s_digit;
         remaining = s_rem;
+        const uint32_t bucket = s_cnt;
         if (shift >= 32) prefix.hi |= (uint64_t)digit << (shift - 32);
         else prefix.lo |= digit << shift;
         __syncthreads();
+        // Early finish: k - remaining keys lie above the chosen bucket and `bucket` keys in it. Once that many fit the
+        // shared-memory sort, the remaining digits need no histogram passes (and no grid barriers): collect them all
+        // and let the sort find the k largest. With continuous gains this happens after the second pass.
+        final_shift = shift;
+        n_cand = (k - remaining) + bucket;
+        if (sort_in_kernel && n_cand <= max_candidates) break;
     }
-    // prefix is now the k-th largest composite key: every key >= prefix is a winner (exactly k of them)
+    // every key whose digits down to `final_shift` are >= those of the prefix is a candidate (n_cand of them; exactly the
+    // k winners when all passes ran)
     for (int64_t i = t0; i < n; i += stride) {
         if (flags[i] & kFlagLeaf) {
             const Key96 key{f64_to_ordered(gain[i]), ~(uint32_t)i};
-            if (key96_ge(key, prefix)) {
+            if (key96_top_ge(key, prefix, final_shift)) {
                 const uint32_t pos = atomicAdd(&st->n_out, 1u);
-                if (pos < k) { win_key[pos] = key.hi; win_idx[pos] = (uint32_t)i; }
+                if (pos < n_cand) { win_key[pos] = key.hi; win_idx[pos] = (uint32_t)i; }
             }
         }
     }
     if (!sort_in_kernel) return;
     fused_grid_barrier(&st->barrier, generation);
     if (blockIdx.x != 0) return;
-    // bitonic sort of the winners, descending composite key = (gain descending, index ascending)
+    // bitonic sort of the candidates, descending composite key = (gain descending, index ascending); the first k win
     uint32_t p2 = 1;
-    while (p2 < k) p2 <<= 1;
+    while (p2 < n_cand) p2 <<= 1;
     uint64_t* s_hi = reinterpret_cast<uint64_t*>(fused_smem);
     uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_hi + p2);
     for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
         // __ldcg: written by other CTAs in this launch
-        s_hi[i] = i < k ? __ldcg(win_key + i) : 0ull;
-        s_lo[i] = i < k ? ~__ldcg(win_idx + i) : 0u;
+        s_hi[i] = i < n_cand ? __ldcg(win_key + i) : 0ull;
+        s_lo[i] = i < n_cand ? ~__ldcg(win_idx + i) : 0u;
     }
     __syncthreads();
     for (uint32_t size = 2; size <= p2; size <<= 1) {
@@ -786,30 +805,35 @@ int s3_select_topk(const double* d_gain, const uint8_t* d_flags, int64_t n_cells
     FusedSelectState* st = nullptr;
     uint64_t* win_key = nullptr;
     uint32_t* win_idx = nullptr;
+    // candidates the in-kernel sort accepts before all digits are resolved (early finish of the radix select)
+    uint32_t max_cand = (uint32_t)(2 * k > 1024 ? 2 * k : 1024);
+    if (max_cand > (uint32_t)kFusedMaxSortK) max_cand = kFusedMaxSortK;
     S3_TRY(scratch.alloc(&st, 1));
-    S3_TRY(scratch.alloc(&win_key, k));
-    S3_TRY(scratch.alloc(&win_idx, k));
+    S3_TRY(scratch.alloc(&win_key, max_cand));
+    S3_TRY(scratch.alloc(&win_idx, max_cand));
     S3_CUDA(cudaMemsetAsync(st, 0, sizeof(FusedSelectState), st_));
     uint32_t p2 = 1;
-    while (p2 < (uint32_t)k) p2 <<= 1;
+    while (p2 < max_cand) p2 <<= 1;
     size_t smem = (size_t)p2 * 12;
     if (smem < kFusedBins * sizeof(uint32_t)) smem = kFusedBins * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        S3_CUDA(cudaFuncSetAttribute(select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kFusedMaxSortK * 12));
-        attr_set = true;
-    }
-    // enough CTAs to stream the cell arrays, never more than one per SM (co-residency of the grid barrier)
+    // function attributes are per device: set it on every call (cheap) instead of once per process
+    S3_CUDA(cudaFuncSetAttribute(select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedMaxSortK * 12));
+    // enough CTAs to stream the cell arrays, never more than one per SM of THIS device (co-residency of the grid barrier)
+    int dev = 0, sms = kNumSMs;
+    S3_CUDA(cudaGetDevice(&dev));
+    S3_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = (int)ceil_div(n_cells, (int64_t)kFusedThreads * 8);
-    if (grid > kNumSMs) grid = kNumSMs;
+    if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
     uint32_t k32 = (uint32_t)k;
     int sort_in_kernel = 1;
     void* args[] = {(void*)&d_gain, (void*)&d_flags, (void*)&n_cells, (void*)&k32, (void*)&st, (void*)&win_key,
-                    (void*)&win_idx, (void*)&d_out, (void*)&sort_in_kernel};
-    S3_CUDA(cudaLaunchCooperativeKernel((const void*)select_fused_kernel, dim3((unsigned)grid), dim3(kFusedThreads), args,
-                                        smem, st_));
+                    (void*)&win_idx, (void*)&d_out, (void*)&sort_in_kernel, (void*)&max_cand};
+    if (cudaLaunchCooperativeKernel((const void*)select_fused_kernel, dim3((unsigned)grid), dim3(kFusedThreads), args,
+                                    smem, st_) != cudaSuccess) {
+        (void)cudaGetLastError();                       // e.g. a MIG slice that cannot co-schedule the grid: multi-kernel path
+        return select_topk_multi(d_gain, d_flags, n_cells, k, d_out, st_);
+    }
     note_launch(1);
     return S3_OK;
 }

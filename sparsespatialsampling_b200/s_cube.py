@@ -146,6 +146,13 @@ class SamplingTree(object):
         self._invalid_h = np.zeros(0, dtype=bool)
         self._lattice_h = np.zeros((0, self._n_dimensions), dtype=np.int64)
         self._scalar = pt.zeros(1, dtype=pt.float64, device=self._device)
+        # pinned staging of the per-iteration transfers: parent list up, (invalid flags, captured-metric sum) down with
+        # ONE synchronisation per iteration
+        self._pin_i64 = pt.empty(1024, dtype=pt.int64, pin_memory=True)
+        self._pin_u8 = pt.empty(8192, dtype=pt.uint8, pin_memory=True)
+        self._pin_f64 = pt.empty(1, dtype=pt.float64, pin_memory=True)
+        self._fuse_metric = False        # set by refine(): the next mask pass also evaluates the captured metric
+        self._fused_sumsq = None
         self._geom_table = GeometryTable(self._geometry, self._device)
 
         self._create_first_cell()
@@ -255,7 +262,10 @@ class SamplingTree(object):
         n_new = n_par * self._nch
         self._reserve(first + n_new)
         par_h = np.asarray(parents, dtype=np.int64)
-        par_d = pt.from_numpy(par_h).to(self._device)
+        if n_par > self._pin_i64.numel():
+            self._pin_i64 = pt.empty(2 * n_par, dtype=pt.int64, pin_memory=True)
+        self._pin_i64[:n_par].numpy()[:] = par_h         # (the previous iteration's copy was synchronised)
+        par_d = self._pin_i64[:n_par].to(self._device, non_blocking=True)
         with pt.cuda.device(self._device):
             _lib.check(self._lib.s3_cells_refine(_lib.ptr(self._center), _lib.ptr(self._level),
                                                  _lib.ptr(self._lattice), _lib.ptr(self._flags), _lib.ptr(par_d), n_par,
@@ -359,7 +369,21 @@ class SamplingTree(object):
                                                tab.n, only, int(refine_geometry), apply, _lib.ptr(out),
                                                _lib.ptr(self._flags), _lib.ptr(self._gain), tab.stl_geoms, tab.stl_meta,
                                                self._stream()))
-        res = out[:n].cpu().numpy().astype(bool)
+            fuse = self._fuse_metric and apply and not tab.custom
+            if fuse:
+                # the mask kernel has removed the invalid children from the leaves on the device: the captured metric
+                # (s_cube.py:317-336) follows in the same stream and comes back with the flags -- one sync, not two
+                _lib.check(self._lib.s3_leaf_sumsq(_lib.ptr(self._metric_d), _lib.ptr(self._flags), self._n_cells,
+                                                   _lib.ptr(self._scalar), self._stream()))
+            if n > self._pin_u8.numel():
+                self._pin_u8 = pt.empty(2 * n, dtype=pt.uint8, pin_memory=True)
+            self._pin_u8[:n].copy_(out[:n], non_blocking=True)
+            if fuse:
+                self._pin_f64.copy_(self._scalar, non_blocking=True)
+            pt.cuda.current_stream(self._device).synchronize()
+        self._fuse_metric = False
+        self._fused_sumsq = float(self._pin_f64[0]) if fuse else None
+        res = self._pin_u8[:n].numpy().astype(bool)
         if tab.custom:
             res = self._mask_custom(cells, res, refine_geometry, only, apply)
         return res
@@ -439,10 +463,14 @@ class SamplingTree(object):
 
     def _compute_captured_metric(self) -> bool:
         # s_cube.py:317-336; the prediction at a leaf centre is the cell's stored metric (s_cube.py:241)
-        with pt.cuda.device(self._device):
-            _lib.check(self._lib.s3_leaf_sumsq(_lib.ptr(self._metric_d), _lib.ptr(self._flags), self._n_cells,
-                                               _lib.ptr(self._scalar), self._stream()))
-        ratio = float(np.sqrt(self._scalar.item())) / self._target_norm
+        if self._fused_sumsq is not None:                # evaluated right behind the mask kernel of this iteration
+            sumsq, self._fused_sumsq = self._fused_sumsq, None
+        else:
+            with pt.cuda.device(self._device):
+                _lib.check(self._lib.s3_leaf_sumsq(_lib.ptr(self._metric_d), _lib.ptr(self._flags), self._n_cells,
+                                                   _lib.ptr(self._scalar), self._stream()))
+            sumsq = self._scalar.item()
+        ratio = float(np.sqrt(sumsq)) / self._target_norm
         self._metric.append(ratio)
         return ratio < self._min_metric
 
@@ -516,7 +544,9 @@ class SamplingTree(object):
                         self._topo.refresh_siblings([i])      # s_cube.py:611
                     nb_to_refine_as_well = set(self._check_nb(i))
                     to_refine.update(self._check_constraint(nb_to_refine_as_well))
+            self._fuse_metric = self._n_cells_max is None
             self._remove_invalid_cells(self._refine_cells(list(to_refine)))
+            self._fuse_metric = False
 
             if self._n_cells_max is None:
                 self._compute_captured_metric()
