@@ -151,8 +151,14 @@ class SamplingTree(object):
         self._pin_i64 = pt.empty(1024, dtype=pt.int64, pin_memory=True)
         self._pin_u8 = pt.empty(8192, dtype=pt.uint8, pin_memory=True)
         self._pin_f64 = pt.empty(1, dtype=pt.float64, pin_memory=True)
+        self._pin_sel = pt.empty(1024, dtype=pt.int64, pin_memory=True)
+        self._sel_d = pt.empty(1024, dtype=pt.int64, device=self._device)
+        self._stream_obj, self._stream_ptr, self._ptr_cache = None, None, {}
+        self._mask_out = pt.empty(8192, dtype=pt.uint8, device=self._device)
         self._fuse_metric = False        # set by refine(): the next mask pass also evaluates the captured metric
         self._fused_sumsq = None
+        self._speculate_k = 0            # set by refine(): the next mask pass also selects the cells of the NEXT iteration
+        self._spec_selection = None
         self._geom_table = GeometryTable(self._geometry, self._device)
 
         self._create_first_cell()
@@ -168,7 +174,24 @@ class SamplingTree(object):
         fn(*args)
 
     def _stream(self):
-        return _lib.stream_ptr()
+        # the C-ABI calls of one refine() run are all queued on the stream that was current when it started
+        # (torch.cuda.current_stream() costs ~15 us per call -- more than a small launch)
+        if self._stream_obj is None:
+            return _lib.stream_ptr()
+        return self._stream_ptr
+
+    def _enter_hot_loop(self) -> None:
+        import ctypes
+        pt.cuda.set_device(self._device)
+        self._stream_obj = pt.cuda.current_stream(self._device)
+        self._stream_ptr = ctypes.c_void_p(self._stream_obj.cuda_stream)
+
+    def _p(self, name: str):
+        """Device pointer of a cell array, cached until the arrays are re-allocated (``_reserve``)."""
+        ptr = self._ptr_cache.get(name)
+        if ptr is None:
+            ptr = self._ptr_cache[name] = _lib.ptr(getattr(self, name))
+        return ptr
 
     def _sumsq(self, x: pt.Tensor) -> float:
         with pt.cuda.device(self._device):
@@ -187,6 +210,7 @@ class SamplingTree(object):
             if old is not None:
                 new[:old.size(0)] = old
             return new
+        self._ptr_cache = {}
         self._center = grow(self._center, (new_cap, d), pt.float64)
         self._level = grow(self._level, (new_cap,), pt.int32)
         self._lattice = grow(self._lattice, (new_cap, d), pt.int32)
@@ -266,13 +290,14 @@ class SamplingTree(object):
             self._pin_i64 = pt.empty(2 * n_par, dtype=pt.int64, pin_memory=True)
         self._pin_i64[:n_par].numpy()[:] = par_h         # (the previous iteration's copy was synchronised)
         par_d = self._pin_i64[:n_par].to(self._device, non_blocking=True)
-        with pt.cuda.device(self._device):
-            _lib.check(self._lib.s3_cells_refine(_lib.ptr(self._center), _lib.ptr(self._level),
-                                                 _lib.ptr(self._lattice), _lib.ptr(self._flags), _lib.ptr(par_d), n_par,
-                                                 first, self._n_dimensions, self._width, self._stream()))
-            _lib.check(self._lib.s3_cells_gain(self._knn.handle, _lib.ptr(self._center), _lib.ptr(self._level), None,
-                                               first, n_new, self._k, self._width, self._gain0, self._sdm_order,
-                                               _lib.ptr(self._metric_d), _lib.ptr(self._gain), self._stream()))
+        if self._stream_obj is None:
+            pt.cuda.set_device(self._device)
+        _lib.check(self._lib.s3_cells_refine(self._p("_center"), self._p("_level"), self._p("_lattice"),
+                                             self._p("_flags"), _lib.ptr(par_d), n_par, first, self._n_dimensions,
+                                             self._width, self._stream()))
+        _lib.check(self._lib.s3_cells_gain(self._knn.handle, self._p("_center"), self._p("_level"), None, first, n_new,
+                                           self._k, self._width, self._gain0, self._sdm_order, self._p("_metric_d"),
+                                           self._p("_gain"), self._stream()))
         self._levels_h[first:first + n_new] = np.repeat(self._levels_h[par_h] + 1, self._nch)
         if self._topo is not None and n_par:
             self._topo_call(self._topo.refine, par_h.copy())   # host replay of _assign_neighbors + _assign_indices
@@ -288,13 +313,11 @@ class SamplingTree(object):
         if n_par:
             self._current_max_level = max(self._current_max_level, int(self._levels_h[par_h].max()) + 1)
 
-        # leaf-set bookkeeping exactly as the reference does it (s_cube.py:877-899, :243-251)
-        all_parents, all_children = set(), set()
-        new_index = first
-        for i in parents:
-            all_children.update(list(range(new_index, new_index + self._nch)))
-            all_parents.add(i)
-            new_index += self._nch
+        # leaf-set bookkeeping exactly as the reference does it (s_cube.py:877-899, :243-251): the reference fills
+        # `all_children` / `all_parents` parent by parent; the same insertion sequence in one call gives the same sets
+        # (identical hash-table layout, hence identical iteration order further on)
+        all_children = set(range(first, first + n_new))
+        all_parents = set(parents)
         self._leaf_cells -= all_parents
         self._leaf_cells.update(all_children)
         self._n_cells += n_new
@@ -355,7 +378,9 @@ class SamplingTree(object):
         returns a bool array aligned with ``cells``. In normal mode the device state is updated as well.
         """
         n = len(cells)
-        out = pt.empty((max(n, 1),), dtype=pt.uint8, device=self._device)
+        if n > self._mask_out.numel():
+            self._mask_out = pt.empty(2 * n, dtype=pt.uint8, device=self._device)
+        out = self._mask_out
         if isinstance(cells, range):
             cells_d, first = None, cells.start
         else:
@@ -363,27 +388,42 @@ class SamplingTree(object):
         only = -1 if geometry_no is None else int(geometry_no)
         apply = 0 if refine_geometry else 1
         tab = self._geom_table
-        with pt.cuda.device(self._device):
-            _lib.check(self._lib.s3_cells_mask(_lib.ptr(self._center), _lib.ptr(self._level), _lib.ptr(cells_d), first, n,
-                                               self._n_dimensions, self._width, _lib.ptr(tab.hdr), _lib.ptr(tab.par),
-                                               tab.n, only, int(refine_geometry), apply, _lib.ptr(out),
-                                               _lib.ptr(self._flags), _lib.ptr(self._gain), tab.stl_geoms, tab.stl_meta,
-                                               self._stream()))
-            fuse = self._fuse_metric and apply and not tab.custom
-            if fuse:
-                # the mask kernel has removed the invalid children from the leaves on the device: the captured metric
-                # (s_cube.py:317-336) follows in the same stream and comes back with the flags -- one sync, not two
-                _lib.check(self._lib.s3_leaf_sumsq(_lib.ptr(self._metric_d), _lib.ptr(self._flags), self._n_cells,
-                                                   _lib.ptr(self._scalar), self._stream()))
-            if n > self._pin_u8.numel():
-                self._pin_u8 = pt.empty(2 * n, dtype=pt.uint8, pin_memory=True)
-            self._pin_u8[:n].copy_(out[:n], non_blocking=True)
-            if fuse:
-                self._pin_f64.copy_(self._scalar, non_blocking=True)
-            pt.cuda.current_stream(self._device).synchronize()
+        if self._stream_obj is None:
+            pt.cuda.set_device(self._device)
+        stream = self._stream()
+        _lib.check(self._lib.s3_cells_mask(self._p("_center"), self._p("_level"), _lib.ptr(cells_d), first, n,
+                                           self._n_dimensions, self._width, _lib.ptr(tab.hdr), _lib.ptr(tab.par),
+                                           tab.n, only, int(refine_geometry), apply, _lib.ptr(out),
+                                           self._p("_flags"), self._p("_gain"), tab.stl_geoms, tab.stl_meta, stream))
+        fuse = self._fuse_metric and apply and not tab.custom
+        if fuse:
+            # the mask kernel has removed the invalid children from the leaves on the device: the captured metric
+            # (s_cube.py:317-336) follows in the same stream and comes back with the flags -- one sync, not two
+            _lib.check(self._lib.s3_leaf_sumsq(self._p("_metric_d"), self._p("_flags"), self._n_cells,
+                                               _lib.ptr(self._scalar), stream))
+        spec_k = self._speculate_k if (apply and not tab.custom) else 0
+        if spec_k:
+            # gains and leaf flags of the next iteration are final on the device at this point: its top-k selection
+            # (s_cube.py:601-602) is queued here as well and returns with the same synchronisation. If the loop
+            # stops instead, the result is dropped.
+            if spec_k > self._sel_d.numel():
+                self._sel_d = pt.empty(2 * spec_k, dtype=pt.int64, device=self._device)
+            _lib.check(self._lib.s3_select_topk(self._p("_gain"), self._p("_flags"), self._n_cells, spec_k,
+                                                _lib.ptr(self._sel_d), stream))
+            if spec_k > self._pin_sel.numel():
+                self._pin_sel = pt.empty(2 * spec_k, dtype=pt.int64, pin_memory=True)
+            self._pin_sel[:spec_k].copy_(self._sel_d[:spec_k], non_blocking=True)
+        if n > self._pin_u8.numel():
+            self._pin_u8 = pt.empty(2 * n, dtype=pt.uint8, pin_memory=True)
+        self._pin_u8[:n].copy_(out[:n], non_blocking=True)
+        if fuse:
+            self._pin_f64.copy_(self._scalar, non_blocking=True)
+        (self._stream_obj or pt.cuda.current_stream(self._device)).synchronize()
         self._fuse_metric = False
+        self._speculate_k = 0
+        self._spec_selection = self._pin_sel[:spec_k].tolist() if spec_k else None
         self._fused_sumsq = float(self._pin_f64[0]) if fuse else None
-        res = self._pin_u8[:n].numpy().astype(bool)
+        res = self._pin_u8[:n].numpy().astype(bool)          # (a copy: the pinned buffer is re-used)
         if tab.custom:
             res = self._mask_custom(cells, res, refine_geometry, only, apply)
         return res
@@ -425,8 +465,10 @@ class SamplingTree(object):
             # so the reference marks no cell at all. Mirrored, not "fixed".
             return None
         if isinstance(_refined_cells, range):
-            order = list({c for c in _refined_cells})            # the reference passes a set comprehension
             flags = self._mask(_refined_cells, _refine_geometry, _geometry_no)
+            if not flags.any():
+                return None                                      # no cell to drop (the common case): nothing to order
+            order = list({c for c in _refined_cells})            # the reference passes a set comprehension
             lookup = dict(zip(_refined_cells, flags.tolist()))
             result = [c if lookup[c] else None for c in order]
         else:
@@ -467,7 +509,7 @@ class SamplingTree(object):
             sumsq, self._fused_sumsq = self._fused_sumsq, None
         else:
             with pt.cuda.device(self._device):
-                _lib.check(self._lib.s3_leaf_sumsq(_lib.ptr(self._metric_d), _lib.ptr(self._flags), self._n_cells,
+                _lib.check(self._lib.s3_leaf_sumsq(self._p("_metric_d"), self._p("_flags"), self._n_cells,
                                                    _lib.ptr(self._scalar), self._stream()))
             sumsq = self._scalar.item()
         ratio = float(np.sqrt(sumsq)) / self._target_norm
@@ -503,15 +545,19 @@ class SamplingTree(object):
         k = min(k, len(self._leaf_cells))
         if k <= 0:
             return []
+        spec, self._spec_selection = self._spec_selection, None
+        if spec is not None and len(spec) == k:
+            return spec                                  # selected behind the previous iteration's mask pass
         out = pt.empty((k,), dtype=pt.int64, device=self._device)
         with pt.cuda.device(self._device):
-            _lib.check(self._lib.s3_select_topk(_lib.ptr(self._gain), _lib.ptr(self._flags), self._n_cells, k,
+            _lib.check(self._lib.s3_select_topk(self._p("_gain"), self._p("_flags"), self._n_cells, k,
                                                 _lib.ptr(out), self._stream()))
         return out.cpu().tolist()
 
     def refine(self) -> None:
         # s_cube.py:563-667
         logger.info("Starting grid generation.")
+        self._enter_hot_loop()
         self._refine_uniform()
         iteration_count = 0
         self._n_cells_after_uniform = len(self._leaf_cells)
@@ -545,8 +591,16 @@ class SamplingTree(object):
                     nb_to_refine_as_well = set(self._check_nb(i))
                     to_refine.update(self._check_constraint(nb_to_refine_as_well))
             self._fuse_metric = self._n_cells_max is None
-            self._remove_invalid_cells(self._refine_cells(list(to_refine)))
+            new_cells = self._refine_cells(list(to_refine))
+            # the number of cells the next iteration selects is known already when cells_per_iter is constant and the
+            # leaves cannot run out: min(cells_per_iter, n_cells, n_leaves) (s_cube.py:601 and heapq.nlargest)
+            k_next = min(self._cells_per_iter, self._n_cells)
+            constant = self._cells_per_iter_start == self._cells_per_iter_end or self._n_cells_max is not None
+            if constant and len(self._leaf_cells) - len(new_cells) >= k_next > 0:
+                self._speculate_k = k_next
+            self._remove_invalid_cells(new_cells)
             self._fuse_metric = False
+            self._speculate_k = 0
 
             if self._n_cells_max is None:
                 self._compute_captured_metric()
