@@ -23,6 +23,7 @@ import logging
 import math
 from typing import Tuple
 
+import numpy as np
 import torch as pt
 
 from . import _lib
@@ -133,15 +134,72 @@ def compute_svd(data_matrix: pt.Tensor, cell_area: pt.Tensor, rank: int = None, 
     return s_out, u, v_out
 
 
+EIG_METHOD = "auto"          # "auto": top-r subspace iteration when rank << T, else the full eigh; "eigh": always full
+
+
+def top_eigenpairs(g: pt.Tensor, r: int, tol: float = 1e-7, max_iter: int = 40):
+    """
+    The ``r`` largest eigenpairs of the symmetric positive semi-definite ``g`` (fp64 ``[T, T]``) by blocked subspace
+    iteration with a Rayleigh-Ritz step per sweep: ``Z = G Q`` (fp64 GEMM), ``H = Q^T Z`` (``b x b``), ``H = W diag(w)
+    W^T``, ``Q <- orth(Z W)`` by Cholesky-QR (the Ritz rotation makes the columns of ``Z W`` nearly orthogonal, so the
+    Cholesky factor is well conditioned). Block size ``b = r + max(8, r / 2)``. Stops when the residuals
+    ``||G x_i - w_i x_i|| <= tol * w_i`` for the first ``r`` pairs (eigenvalue error <= residual^2 / gap, vector error
+    <= residual / gap). Returns ``None`` -- the caller falls back to ``torch.linalg.eigh`` -- if ``r`` is not small
+    against ``T``, or as soon as the observed contraction rate of the residuals says that ``max_iter`` sweeps will not
+    do (slowly decaying spectra: a flat tail inside the first ``r`` pairs).
+    A full ``eigh`` of a 2000 x 2000 Gram matrix takes 27.7 ms on a B200 (62 % of compute_svd at C5, VERDICT r1);
+    the examples of the reference ask for 20-150 modes.
+    """
+    t = g.size(0)
+    b = r + max(8, r // 2)
+    if 4 * b > t:
+        return None
+    gen = pt.Generator(device=g.device).manual_seed(0)
+    q = pt.randn((t, b), dtype=pt.float64, device=g.device, generator=gen)
+    q, _ = pt.linalg.qr(g @ q)
+    history = []
+    for sweep in range(max_iter):
+        z = g @ q
+        h = q.T @ z
+        w, rot = pt.linalg.eigh(0.5 * (h + h.T))
+        w, rot = pt.flip(w, dims=(0,)), pt.flip(rot, dims=(1,))
+        x, gx = q @ rot, z @ rot                               # Ritz vectors and G times them
+        res = (gx - x * w.unsqueeze(0)).norm(dim=0)
+        excess = float((res[:r] / (tol * w[:r].clamp_min(0.0) + 1e-13 * w[0])).max())
+        if excess <= 1.0:
+            return w[:r], x[:, :r]
+        history.append(excess)
+        if sweep >= 6:
+            rate = (history[-1] / history[-4]) ** (1.0 / 3.0)          # contraction per sweep, last three sweeps
+            if rate >= 0.98 or np.log(excess) / -np.log(rate) > (max_iter - 1 - sweep):
+                return None
+        # next basis: orth(G X). Columns of G X are ~ w_i x_i: scale, then Cholesky-QR twice
+        y = gx / w.clamp_min(1e-300 * float(w[0]) + 1e-300).unsqueeze(0)
+        for _ in range(2):
+            chol, info = pt.linalg.cholesky_ex(y.T @ y)
+            if int(info) != 0:
+                y, _ = pt.linalg.qr(y)
+                break
+            y = pt.linalg.solve_triangular(chol, y.T, upper=False).T
+        q = y
+    return None
+
+
 def _factor(a: pt.Tensor, mean: pt.Tensor, g: pt.Tensor, rank, n_modes, rows_total: int, vol: pt.Tensor, vol_div: int,
             method: str):
     """Eigen-decomposition of the (summed) Gram matrix and projection of the rows held in ``a``."""
     t = a.size(1)
-    lam, vec = pt.linalg.eigh(g)                       # ascending, fp64
-    lam = pt.flip(lam, dims=(0,))
-    vec = pt.flip(vec, dims=(1,))
-    s_all = lam.clamp_min(0.0).sqrt()
     r_max = min(rows_total, t)
+    top = None
+    if rank is not None and EIG_METHOD == "auto":
+        top = top_eigenpairs(g, max(1, min(int(rank), r_max)))
+    if top is not None:
+        lam, vec = top                                 # descending, only the pairs that were asked for
+    else:
+        lam, vec = pt.linalg.eigh(g)                   # ascending, fp64
+        lam = pt.flip(lam, dims=(0,))
+        vec = pt.flip(vec, dims=(1,))
+    s_all = lam.clamp_min(0.0).sqrt()
     if rank is None:
         r = optimal_rank(s_all[:r_max], rows_total, t)
     else:

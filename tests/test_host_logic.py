@@ -106,3 +106,24 @@ def test_surface_geometry_oracle_meets_reference_unit_tests(tmp_path):
                for n in ("cell_outside_2D", "cell_inside_2D", "cell_partially_2D")]
         assert got == expected
     assert g.GeometrySTL3D("cube", False, str(p)).device_params()[2] == 12
+
+
+def test_top_eigenpairs_subspace_iteration_and_fallback():
+    """svd.top_eigenpairs (pure torch, runs on the CPU as well): exact leading eigenpairs for decaying spectra, early
+    bail-out (None -> full eigh) for a flat tail inside the requested pairs and when r is not small against T."""
+    from sparsespatialsampling_b200.svd import top_eigenpairs
+    pt.manual_seed(0)
+    t = 600
+    u, _ = pt.linalg.qr(pt.randn(t, t, dtype=pt.float64))
+    decaying = (1.0 / pt.arange(1, t + 1, dtype=pt.float64)) ** 3
+    g = (u * decaying) @ u.T
+    for r in (4, 30):
+        w, x = top_eigenpairs(g, r)
+        ref_w, ref_v = pt.linalg.eigh(g)
+        ref_w, ref_v = ref_w.flip(0)[:r], ref_v.flip(1)[:, :r]
+        assert float(((w - ref_w).abs() / ref_w).max()) < 1e-10
+        assert float((x.T @ x - pt.eye(r, dtype=pt.float64)).abs().max()) < 1e-10
+        assert float((x * ref_v).sum(0).abs().min()) > 1 - 1e-8          # same vectors up to sign
+    flat = pt.cat([pt.logspace(0, -3, 10, dtype=pt.float64), 1e-4 * pt.logspace(0, -2, t - 10, dtype=pt.float64)])
+    assert top_eigenpairs((u * flat) @ u.T, 30) is None                   # slowly decaying tail: not worth iterating
+    assert top_eigenpairs(g, 200) is None                                 # r not small against T

@@ -168,3 +168,26 @@ def test_tensor_core_projection_matches_fp64(cuda, m, t, r, vol_div):
     assert float((u1.double() - ref).abs().max()) <= 5e-3 * scale           # single TF32 pass
     us = svd.project(a, mean, w)                                            # fp32 CUDA-core kernel
     assert float((us.double() - ref).abs().max()) <= 2e-5 * scale
+
+
+def test_small_rank_takes_the_subspace_eigensolver_and_agrees_with_eigh(cuda):
+    """compute_svd(rank << T): top-r eigenpairs of the Gram matrix by subspace iteration (svd.top_eigenpairs) instead of
+    the full T x T eigh; same factors."""
+    from sparsespatialsampling_b200 import svd
+    a, area = _low_rank_field(20000, 640, 6, seed=3)
+    ad, aread = pt.from_numpy(a).cuda(), pt.from_numpy(area).cuda()
+    mean = svd.row_means(ad)
+    g = svd.gram(ad, mean, aread.float(), 1, "tc3")
+    assert svd.top_eigenpairs(g, 8) is not None                           # the iteration converges on this spectrum
+    outs = {}
+    for how in ("auto", "eigh"):
+        svd.EIG_METHOD = how
+        try:
+            outs[how] = svd.compute_svd(ad, aread, rank=8)
+        finally:
+            svd.EIG_METHOD = "auto"
+    (s1, u1, v1), (s2, u2, v2) = outs["auto"], outs["eigh"]
+    assert float(((s1 - s2).abs() / s2[0]).max()) < 1e-6
+    for i in range(6):
+        assert abs(float(v1[:, i] @ v2[:, i])) > 1 - 1e-6
+        assert abs(float(u1[:, i] @ u2[:, i])) / float(u1[:, i].norm() * u2[:, i].norm()) > 1 - 1e-5
