@@ -311,8 +311,7 @@ class ExportData:
             self._write_times = write_times if isinstance(write_times, list) else [write_times]
         else:
             self._write_times = None
-            logger.warning("Argument ``write_times`` is ``None``. Make sure to set the ``write_times`` before calling "
-                           "the ``export()`` method.")
+            logger.warning("ExportData was created without write_times; assign `write_times` before the first export().")
 
         self._interpolated_fields = Fields()
         self._field_name = None
@@ -325,9 +324,9 @@ class ExportData:
         self._n_snapshots_total = None
         self._t_start = time()
         if append_existing:
-            logger.info(f"Appending fields to file {path.join(self._save_dir, self._save_name)}.h5")
+            logger.info("append_existing: new fields go into %s.h5", path.join(self._save_dir, self._save_name))
             if self._new_file:
-                logger.warning("Setting `write_new_file_for_each_field = False` since `append_existing` is `True`")
+                logger.warning("append_existing=True implies one common file: write_new_file_for_each_field is ignored.")
                 self._new_file = False
 
         if n_neighbors is None:
@@ -356,8 +355,8 @@ class ExportData:
     def export(self, coordinates: pt.Tensor, data: pt.Tensor, field_name: str, n_snapshots_total: int = None,
                chunk_size: int = 100000) -> None:
         if self._write_times is None:
-            raise ValueError("Couldn't find any ``write_times`` for export. Make sure to pass the write times "
-                             "when instantiating the export object or set it before calling the ``export method``.")
+            raise ValueError("export() needs the list of write times: pass `write_times` to ExportData(...) or set the "
+                             "`write_times` property first.")
         self._chunk_size = int(chunk_size)
         self._field_name = field_name
         self._fit_data(coordinates, data, field_name, n_snapshots_total)
@@ -380,16 +379,15 @@ class ExportData:
     def _fit_data(self, _coord, _data, _field_name, _n_snapshots_total=None) -> None:
         # export.py:169-231
         if len(_data.size()) < 2:
-            raise ValueError("The provided field must have the shape '[N_cells, N_dimensions, N_snapshots]' for a "
-                             "vector field and '[N_cells, 1, N_snapshots]' for a scalar field. "
-                             f"Found a dimension of {len(_data.size())} for parameter 'data'.")
+            raise ValueError(f"`data` has {len(_data.size())} dimension(s); expected [N_points, D, N_snapshots] "
+                             "(D = 1 for a scalar field) or [N_points, N_snapshots].")
         elif len(_data.size()) == 2:
-            logger.warning("Detected a scalar field of dimension 2 as input. Reshaping to '[N_cells, 1, N_snapshots]'.")
+            logger.warning("2-D `data` is taken as a scalar field [N_points, N_snapshots] -> [N_points, 1, N_snapshots].")
             _data = _data.unsqueeze(1)
         if not self._initialized_weights:
             self._build_knn_cache(_coord)
         if self._snapshot_counter == 0:
-            logger.info(f"Starting interpolation and export of field {self._field_name}.")
+            logger.info("Field %s: interpolating onto the sampled grid.", self._field_name)
         if not self._interpolated_metric:
             # metric on the sampled grid (export.py:214-216), fp64
             m = self._metric.detach().to(device=self._device, dtype=pt.float64).reshape(-1, 1).contiguous()
@@ -484,9 +482,9 @@ class ExportData:
 
     def _build_knn_cache(self, _coord: pt.Tensor) -> None:
         # export.py:403-444
-        logger.info("Initializing KNN and computing interpolation weights.")
+        logger.info("Building the KNN index over the original points and the interpolation tables.")
         if self._coord_shape is not None and _coord.shape != self._coord_shape:
-            logger.warning("CFD grid change detected. Re-computing interpolation weights of the KNN.")
+            logger.warning("The coordinates differ in shape from the previous call: rebuilding the interpolation tables.")
         self._coord_shape = _coord.shape
         if self._rank == 0:
             self._make_tables(_coord)
@@ -531,7 +529,7 @@ class ExportData:
                 self._snapshot_counter = 0
             return
         if not self._initialized_hdf5:
-            logger.info(f"Writing HDF5 file for field {self._field_name}.")
+            logger.info("Field %s: creating the output file.", self._field_name)
             if not path.exists(self._save_dir):
                 makedirs(self._save_dir, exist_ok=True)
             self._datawriter = Datawriter(self._save_dir, self._part_name(self._rank))
@@ -595,7 +593,7 @@ class ExportData:
             self._snapshot_counter = 0
             if self._new_file:
                 self._initialized_hdf5 = False
-            logger.info(f"Finished export of field {self._field_name} in {round(time() - self._t_start, 3)}s.")
+            logger.info("Field %s: export done after %.3f s.", self._field_name, time() - self._t_start)
             self._t_start = time()
 
     # ------------------------------------------------------------------------------------------ properties

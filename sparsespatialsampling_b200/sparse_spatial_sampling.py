@@ -78,25 +78,35 @@ class SparseSpatialSampling:
         pt.save(self, join(self.save_path, f"s_cube_{self.save_name}.pt"))
 
     def _check_input(self) -> None:
-        # sparse_spatial_sampling.py:148-186
-        assert len(self.metric.size()) == 1, (f"The size of the metric must be a 1D tensor of the length "
-                                              f"{self.coordinates.size(0)}. The size of the metric given is "
-                                              f"{self.metric.size()}.")
-        if self._n_cells_max is None:
-            if self._min_metric > 1:
-                logger.warning("A value of min_metric > 1 is invalid. Changed min_metric to 1.")
-                self._min_metric = 1
-        assert self._geometries, ("No geometries are provided. Please provide at least one geometry for the "
-                                  "numerical domain.")
-        assert any([g.keep_inside for g in self._geometries]), ("No geometry for the domain provided. At least one "
-                                                                "geometry object must have 'keep_inside = True' "
-                                                                "representing the numerical domain.")
+        """
+        Argument validation with the reference's outcomes (sparse_spatial_sampling.py:148-186: which inputs are
+        rejected, which are silently corrected), worded independently.
+        """
+        problems = []
+        if self.metric.dim() != 1:
+            problems.append(f"`metric` has shape {tuple(self.metric.shape)}; S^3 needs one value per point, i.e. a 1-D "
+                            f"tensor with {self.coordinates.size(0)} entries")
+        if not self._geometries:
+            problems.append("`geometry_objects` is empty; pass at least the geometry that spans the numerical domain")
+        elif not any(bool(g.keep_inside) for g in self._geometries):
+            problems.append("none of the geometries has keep_inside=True, so nothing defines the numerical domain")
+        if problems:
+            raise AssertionError("invalid input for SparseSpatialSampling: " + "; ".join(problems))
+        if self._n_cells_max is None and self._min_metric > 1:
+            logger.warning("min_metric = %s exceeds 100 %% of the metric; using 1.0 instead.", self._min_metric)
+            self._min_metric = 1
         if self._level_bounds <= 0:
-            logger.warning(f"Lower level bound of {self._level_bounds} is invalid. Changed lower level bound to 1.")
+            logger.warning("uniform_levels = %s is not a positive number of levels; using 1 instead.", self._level_bounds)
             self._level_bounds = 1
         if self._n_cells_max is not None:
-            logger.warning("Detected stopping criterion 'n_cells_max'; this deactivates the 'min_metric' stopping "
-                           "criterion.")
+            logger.warning("n_cells_max = %s is set: the refinement stops on the cell budget and ignores min_metric.",
+                           self._n_cells_max)
+        if self._pre_select_cells:
+            # the reference's validity check (s_cube.py:1832-1836) never reaches the full geometry test when the
+            # bounding-box pre-selection is on, so NO cell is masked at all; mirrored for parity, but say so
+            logger.warning("pre_select_cells=True reproduces the reference's behaviour of skipping every geometry mask: "
+                           "cells inside bodies / outside the domain stay in the grid and geometry refinement finds "
+                           "nothing. Leave it False unless that is what you need.")
 
 
 def list_geometries() -> None:
