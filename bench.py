@@ -341,6 +341,10 @@ def run_ours(args):
         pt.cuda.synchronize()
         t_tables = time.time() - t0
     barrier()
+    if world > 1:        # NCCL builds its broadcast channels on first use (20-35 ms on an 8-GPU box), per message
+        # size class: not the tables' cost -- one untimed broadcast of the same size first
+        KnnTables.share(tables, dev, src=0)
+    barrier()
     b0, b1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
     b0.record()
     centers = broadcast_grid(centers, 2, dev, src=0)
@@ -407,8 +411,11 @@ def run_ours(args):
     launches = _lib.launch_count() - launches0 - 2 * warmup
     ms_step = ms_total / args.steps
     units_step = n_cells * 3 * N_SNAP                       # whole job: all ranks together interpolate the full batch
-    # the one-off table broadcast is charged to the K timed steps (one export job = K passes here)
-    value = units_step * args.steps / ((ms_total + bcast_ms) * 1e-3)
+    # `value`: the K timed steps, as the bench contract defines it. The one-off broadcast of grid + tables (once per
+    # ExportData object, whatever the number of fields / batches exported afterwards) is reported beside it, and as
+    # `value_incl_table_broadcast` charged in full to these K steps.
+    value = units_step / (ms_step * 1e-3)
+    value_incl_bcast = units_step * args.steps / ((ms_total + bcast_ms) * 1e-3)
     out_p, out_u = sets[0][2], sets[0][3]
     check_p, check_u = out_p.clone(), out_u.clone()
 
@@ -542,8 +549,9 @@ def run_ours(args):
                    "l2_policy": f"{n_rot} rotating input/output buffer set(s): {step_bytes * n_rot / 1e6:.0f} MB touched "
                                 f"between re-uses of a byte vs 126 MB L2",
                    "sharding": "one batch, snapshot window per rank (strong scaling); grid + KNN tables broadcast once "
-                               "over NCCL, its time is charged to the K timed steps",
-                   "tables_broadcast_ms": bcast_ms,
+                               "over NCCL before the timed steps (tables_broadcast_ms; value_incl_table_broadcast charges "
+                               "it to the K timed steps)",
+                   "tables_broadcast_ms": bcast_ms, "value_incl_table_broadcast": value_incl_bcast,
                    "host_cores_bound_to_gpu_numa_node": len(numa_cores) if numa_cores else None,
                    "tune": args.tune or None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -20,7 +20,7 @@ from sparsespatialsampling_b200.export import KnnTables
 from sparsespatialsampling_b200.interpolate import alloc_snapshots
 from sparsespatialsampling_b200.knn import KnnIndex
 
-DEFAULTS = {1: 8, 2: 0, 3: -1, 4: 0, 5: -1, 6: -1, 7: 1, 9: 1}
+DEFAULTS = {1: 8, 2: 0, 3: -1, 4: 0, 5: -1, 6: -1, 7: 0, 9: 1}
 VARIANTS = ["", "9=0", "9=0,6=0", "9=0,6=0,2=1", "6=-1,3=0", "2=2", "1=4", "1=16", "4=512", "7=4"]
 OLD_VARIANTS = ["", "7=2", "7=4", "2=2", "2=2,7=2", "6=1,3=1", "6=1,3=1,7=2", "8=2", "8=2,7=2", "8=2,7=4", "8=2,4=512",
             "8=2,7=2,4=512", "8=4", "8=4,7=2", "8=4,4=512", "8=4,4=256", "8=4,1=4", "8=4,1=4,4=512", "8=2,1=4",

@@ -33,7 +33,7 @@ static int g_chunk_cols = 0;       // key 4: columns per blockIdx.y window, 0 = 
 static int g_carveout = -1;        // key 5: shared-memory carve-out in percent, -1 = driver default
 static int g_wide = -1;            // key 6: 256-bit loads (fp32 in/out, pointers and pitches multiples of 32 B): -1 = whenever possible
 static int g_dense = 1;            // key 9: 1 = dense fp32 batches with k <= 16 take interp_dense_kernel
-static int g_kunroll = 1;          // key 7: neighbour-loop unroll (row loads in flight per lane): 1 or 4
+static int g_kunroll = 0;          // key 7: neighbour-loop unroll (row loads in flight per lane): 1, 4 or 8; 0 = by row length
 extern int g_tc_seg_kblocks;
 extern int g_tc_flush_segments;
 extern int g_tc_pair;
@@ -244,9 +244,14 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
     const bool wide_ok = vec_ok && MODE == 0 && std::is_same<Tin, float>::value && std::is_same<Tout, float>::value &&
                          (uintptr_t)data % 32 == 0 && (uintptr_t)out % 32 == 0 && g.row_stride % 8 == 0 &&
                          g.comp_stride % 8 == 0 && g.out_row_stride % 8 == 0 && g.out_comp_stride % 8 == 0;
-    const bool wide = wide_ok && g_wide != 0;
-    const int unroll = g_unroll != 0 ? g_unroll : (wide ? (k > 16 ? 2 : 1) : 2);
+    // short rows (time windows of a sharded export): a 256-column warp step would leave most lanes idle
+    const bool wide = wide_ok && (g_wide == 1 || (g_wide < 0 && g.n_cols >= 384));
+    const int unroll = g_unroll != 0 ? g_unroll : (wide ? (k > 16 ? 2 : 1) : (g.n_cols > 128 ? 2 : 1));
     const bool pairs = g_pairs >= 0 ? g_pairs != 0 : (wide || k > 16);
+    // Rows of one or two warp steps (the time windows of a sharded export): the warp is bound by the chain
+    // index -> row load -> FMA, one load latency per neighbour; eight neighbours' loads are issued as a batch there.
+    // Long rows keep one load in flight per warp (more only thrashes the L1, profiles/r2_interp_lab.md).
+    const int kunroll = g_kunroll != 0 ? g_kunroll : (g.n_cols <= 256 ? 8 : 1);
     if constexpr (std::is_same<Tin, float>::value && std::is_same<Tout, float>::value && MODE == 0) {
         if (g_dense && vec_ok && k <= 16 && n_comp == 1 && g.n_cols % 4 == 0 && g.row_stride == g.n_cols &&
             g.out_row_stride == g.n_cols && g_chunk_cols == 0) {
@@ -283,8 +288,9 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
     Tout* o_p = reinterpret_cast<Tout*>(out);
 #define S3_WARPCELL(VV, UU, PP)                                                                                   \
     do {                                                                                                          \
-        auto kern = g_kunroll == 4 ? interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, PP, 4>                    \
-                                   : interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, PP, 1>;                   \
+        auto kern = kunroll == 8 ? interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, PP, 8>                      \
+                  : kunroll == 4 ? interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, PP, 4>                      \
+                                 : interp_warpcell_kernel<Tin, Tw, Tout, VV, MODE, UU, PP, 1>;                     \
         if (g_carveout >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout); \
         kern<<<grid, warps * 32, smem, stream>>>(d_p, idx, w_p, n_cells, k, out_row, o_p, g);                      \
     } while (0)
@@ -324,7 +330,7 @@ extern "C" int s3x_tune(int key, int value) {
         case 5: S3_REQUIRE(value >= -1 && value <= 100, "s3x_tune: carve-out must be -1 or 0..100"); g_carveout = value; return S3_OK;
         case 6: S3_REQUIRE(value >= -1 && value <= 1, "s3x_tune: wide must be -1 (auto), 0 or 1"); g_wide = value; return S3_OK;
         case 9: S3_REQUIRE(value == 0 || value == 1, "s3x_tune: dense kernel must be 0 or 1"); g_dense = value; return S3_OK;
-        case 7: S3_REQUIRE(value == 1 || value == 4, "s3x_tune: neighbour-loop unroll must be 1 or 4"); g_kunroll = value; return S3_OK;
+        case 7: S3_REQUIRE(value == 0 || value == 1 || value == 4 || value == 8, "s3x_tune: neighbour-loop unroll must be 0 (auto), 1, 4 or 8"); g_kunroll = value; return S3_OK;
         case 10: S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3x_tune: K-blocks per TMEM segment must be >= 1"); g_tc_seg_kblocks = value; return S3_OK;
         case 11: S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3x_tune: segments per fp64 flush must be >= 1"); g_tc_flush_segments = value; return S3_OK;
         case 14: S3_REQUIRE(value == 0 || value == 1, "s3x_tune: paired Gram kernel must be 0 or 1"); g_tc_pair = value; return S3_OK;
@@ -356,6 +362,10 @@ extern "C" int s3_interp_gather_strided(const void* d_data, int data_dtype, int6
     if (n_comp > 1 && comp_stride == n_cols && out_comp_stride == n_cols) {
         g.n_cols = n_cols * n_comp;
         n_comp = 1;
+    }
+    if (n_comp == 1) {                      // a single component: its stride means nothing (and must not spoil the alignment tests)
+        g.comp_stride = 0;
+        g.out_comp_stride = 0;
     }
     if (data_dtype == S3_F32 && out_dtype == S3_F32)
         return launch_interp<float, float, float, 0>(d_data, d_idx, d_w, n_cells, k, d_out_row, d_out, n_comp, g, st);

@@ -109,7 +109,9 @@ class KnnTables:
     def default_window(n_src: int, comps: int, t: int) -> int:
         """Snapshots per window: rows of >= 1 KB keep the pitched DMA copies at full PCIe rate in both directions
         (measured on this pool: 256 B rows 46 GB/s with poor overlap, 1 KB rows 53 GB/s with full overlap), at least
-        four windows per batch so the pipeline has something to overlap, at most 4 GB per staging buffer."""
+        four windows per batch so the pipeline has something to overlap -- also for the short batches of a sharded
+        export (one window per batch measured 2x slower at 4 and 8 ranks: the H2D / kernel / D2H overlap is worth more
+        than long DMA rows) --, at most 4 GB per staging buffer."""
         cap = max(32, (int(4e9 / (4 * n_src * comps)) // 32) * 32)
         quarter = max(32, ((t + 3) // 4 + 31) // 32 * 32)
         return max(32, min(256 if t >= 512 else quarter, cap, t))

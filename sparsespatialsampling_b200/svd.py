@@ -161,7 +161,12 @@ def top_eigenpairs(g: pt.Tensor, r: int, tol: float = 1e-7, max_iter: int = 40):
     for sweep in range(max_iter):
         z = g @ q
         h = q.T @ z
-        w, rot = pt.linalg.eigh(0.5 * (h + h.T))
+        if not bool(pt.isfinite(h).all()):
+            return None
+        try:
+            w, rot = pt.linalg.eigh(0.5 * (h + h.T))
+        except RuntimeError:                                   # the small solver gave up: let the full eigh decide
+            return None
         w, rot = pt.flip(w, dims=(0,)), pt.flip(rot, dims=(1,))
         x, gx = q @ rot, z @ rot                               # Ritz vectors and G times them
         res = (gx - x * w.unsqueeze(0)).norm(dim=0)
@@ -171,10 +176,15 @@ def top_eigenpairs(g: pt.Tensor, r: int, tol: float = 1e-7, max_iter: int = 40):
         history.append(excess)
         if sweep >= 6:
             rate = (history[-1] / history[-4]) ** (1.0 / 3.0)          # contraction per sweep, last three sweeps
-            if rate >= 0.98 or np.log(excess) / -np.log(rate) > (max_iter - 1 - sweep):
+            if not np.isfinite(rate) or rate >= 0.98 or np.log(excess) / -np.log(rate) > (max_iter - 1 - sweep):
                 return None
-        # next basis: orth(G X). Columns of G X are ~ w_i x_i: scale, then Cholesky-QR twice
-        y = gx / w.clamp_min(1e-300 * float(w[0]) + 1e-300).unsqueeze(0)
+        # next basis: orth(G X). The columns of G X are ~ w_i x_i: normalise them, then Cholesky-QR twice; directions in
+        # the (numerical) null space of G carry no information -- refresh them with random vectors
+        nrm = gx.norm(dim=0)
+        dead = nrm <= 1e-13 * nrm.max()
+        y = gx / nrm.clamp_min(1e-300).unsqueeze(0)
+        if bool(dead.any()):
+            y[:, dead] = pt.randn((t, int(dead.sum())), dtype=pt.float64, device=g.device, generator=gen) / np.sqrt(t)
         for _ in range(2):
             chol, info = pt.linalg.cholesky_ex(y.T @ y)
             if int(info) != 0:

@@ -180,14 +180,14 @@ def test_time_window_views_with_a_common_line_offset(cuda, offset):
 
 
 @pytest.mark.parametrize("tune", ["1=4", "1=16", "2=1", "2=2", "3=0", "3=1", "4=256", "4=128,2=2", "6=1", "6=1,2=2",
-                                  "6=0", "7=4", "7=4,3=1,2=2", "6=1,7=4", "9=0", "9=0,6=0,2=1"])
+                                  "6=0", "7=4", "7=8", "7=1", "7=4,3=1,2=2", "6=1,7=4", "9=0", "9=0,6=0,2=1"])
 def test_launch_variants_are_bit_identical(cuda, tune):
     """The launch knobs of the A/B harness (warps per CTA, column vectors per step, shared-memory pairs, column
     windows, 256-bit loads, neighbour-loop batching) change scheduling only: same sums in the same order."""
     from sparsespatialsampling_b200 import _lib
     from sparsespatialsampling_b200.interpolate import interp_gather, to_pitched
     cases = [_local_case(3000, 900, 8, 1, 1000, 1), _local_case(3000, 300, 26, 2, 333, 2)]
-    defaults = {1: 8, 2: 0, 3: -1, 4: 0, 6: -1, 7: 1, 9: 1}
+    defaults = {1: 8, 2: 0, 3: -1, 4: 0, 6: -1, 7: 0, 9: 1}
     want = []
     for data, idx, w in cases:
         want.append(interp_gather(to_pitched(pt.from_numpy(data).cuda()), pt.from_numpy(idx).cuda(),

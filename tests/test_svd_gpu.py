@@ -178,16 +178,17 @@ def test_small_rank_takes_the_subspace_eigensolver_and_agrees_with_eigh(cuda):
     ad, aread = pt.from_numpy(a).cuda(), pt.from_numpy(area).cuda()
     mean = svd.row_means(ad)
     g = svd.gram(ad, mean, aread.float(), 1, "tc3")
-    assert svd.top_eigenpairs(g, 8) is not None                           # the iteration converges on this spectrum
+    assert svd.top_eigenpairs(g, 5) is not None                           # converges on the 6 coherent modes ...
+    assert svd.top_eigenpairs(g, 40) is None                              # ... and declines the flat noise tail
     outs = {}
     for how in ("auto", "eigh"):
         svd.EIG_METHOD = how
         try:
-            outs[how] = svd.compute_svd(ad, aread, rank=8)
+            outs[how] = svd.compute_svd(ad, aread, rank=5)
         finally:
             svd.EIG_METHOD = "auto"
     (s1, u1, v1), (s2, u2, v2) = outs["auto"], outs["eigh"]
     assert float(((s1 - s2).abs() / s2[0]).max()) < 1e-6
-    for i in range(6):
+    for i in range(5):
         assert abs(float(v1[:, i] @ v2[:, i])) > 1 - 1e-6
         assert abs(float(u1[:, i] @ u2[:, i])) / float(u1[:, i].norm() * u2[:, i].norm()) > 1 - 1e-5
