@@ -8,7 +8,7 @@ if len(sys.argv) > 2:                     # e.g. 11=128,14=0
     from sparsespatialsampling_b200 import _lib
     for kv in sys.argv[2].split(","):
         key, val = kv.split("=")
-        _lib.check(_lib.load().s3_set_tuning(int(key), int(val)))
+        _lib.tune(int(key), int(val))
 pt.manual_seed(0)
 a = pt.randn(m, t, device="cuda")
 vol = pt.rand(m, device="cuda") + 0.5
