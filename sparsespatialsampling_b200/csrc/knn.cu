@@ -73,9 +73,36 @@ __device__ __forceinline__ uint64_t spread3(uint64_t v) {  // 21 bits -> every 3
     return v;
 }
 
+// Space-filling-curve key of a point. g_curve = 1 (default): Hilbert curve (Skilling's transpose algorithm) -- every run
+// of consecutive points on it is one compact blob, so the 32-point leaves and the 32-leaf nodes of the implicit
+// hierarchy have tight boxes. On the Z (Morton) curve (g_curve = 0) a run that crosses an octant boundary of a high
+// level consists of two far-apart clusters: its box spans the gap, intersects almost every query ball nearby and is
+// never pruned -- the k = 26 search on 10 M points popped ~800 nodes per query that way (profiles/r1_gain_kernel_c4).
+int g_curve = 1;
+
+template <int DIM>
+__device__ __forceinline__ void hilbert_transpose(uint64_t* x, int bits) {
+    const uint64_t m = 1ull << (bits - 1);
+    for (uint64_t q = m; q > 1; q >>= 1) {
+        const uint64_t p = q - 1;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            if (x[i] & q) x[0] ^= p;
+            else { const uint64_t t = (x[0] ^ x[i]) & p; x[0] ^= t; x[i] ^= t; }
+        }
+    }
+#pragma unroll
+    for (int i = 1; i < DIM; ++i) x[i] ^= x[i - 1];
+    uint64_t t = 0;
+    for (uint64_t q = m; q > 1; q >>= 1)
+        if (x[DIM - 1] & q) t ^= q - 1;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) x[i] ^= t;
+}
+
 __global__ void __launch_bounds__(256)
 morton_kernel(const double* __restrict__ coords, int64_t n, int dim, const double* __restrict__ bb,
-              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int curve) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int bits = dim == 2 ? 31 : 21;
@@ -89,8 +116,14 @@ morton_kernel(const double* __restrict__ coords, int64_t n, int dim, const doubl
         if (c > (1ull << bits) - 1) c = (1ull << bits) - 1;
         q[a] = c;
     }
-    uint64_t key = dim == 2 ? (spread2(q[0]) | (spread2(q[1]) << 1))
-                            : (spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2));
+    uint64_t key;
+    if (curve == 1) {
+        if (dim == 2) { hilbert_transpose<2>(q, bits); key = (spread2(q[0]) << 1) | spread2(q[1]); }
+        else { hilbert_transpose<3>(q, bits); key = (spread3(q[0]) << 2) | (spread3(q[1]) << 1) | spread3(q[2]); }
+    } else {
+        key = dim == 2 ? (spread2(q[0]) | (spread2(q[1]) << 1))
+                       : (spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2));
+    }
     keys[i] = key;
     vals[i] = (uint32_t)i;
 }
@@ -254,7 +287,7 @@ static int knn_build_impl(const double* coords, int64_t n, int dim, const double
 
     bbox_partial_kernel<<<nparts, 256, 0, stream>>>(coords, n, dim, partial);
     bbox_final_kernel<<<1, 32, 0, stream>>>(partial, nparts, dim, bb);
-    morton_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(coords, n, dim, bb, ka, va);
+    morton_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(coords, n, dim, bb, ka, va, g_curve);
     S3_LAUNCH_CHECK();
     bool in_a = true;
     S3_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, 64, stream, &in_a));
@@ -367,7 +400,7 @@ int s3_morton_order(const double* d_coords, int64_t n, int dim, int32_t* d_perm,
     S3_TRY(scratch.alloc(&vb, n));
     bbox_partial_kernel<<<nparts, 256, 0, st_>>>(d_coords, n, dim, partial);
     bbox_final_kernel<<<1, 32, 0, st_>>>(partial, nparts, dim, bb);
-    morton_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st_>>>(d_coords, n, dim, bb, ka, va);
+    morton_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st_>>>(d_coords, n, dim, bb, ka, va, g_curve);
     S3_LAUNCH_CHECK();
     bool in_a = true;
     S3_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, 64, st_, &in_a));
