@@ -194,7 +194,7 @@ def main():
     if args.svd or args.name == "C5":
         from sparsespatialsampling_b200 import svd as s3svd
         del data
-        a2 = out.reshape(nc, T)
+        a2 = out.reshape(nc, T).contiguous()
         area = pt.pow(width / pt.pow(2.0, sc.levels.to(device=dev, dtype=pt.float64).reshape(-1)), d).to(pt.float32)
         mean = s3svd.row_means(a2)
         times = {}

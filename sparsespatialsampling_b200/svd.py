@@ -54,6 +54,7 @@ def _as_device_matrix(data_matrix: pt.Tensor, dev) -> pt.Tensor:
 def row_means(a: pt.Tensor) -> pt.Tensor:
     """Temporal mean of every row of ``a`` ([M, T] fp32 on the device)."""
     lib = _lib.load()
+    a = a.contiguous()                    # (a pitched export result is a strided view: the SVD kernels want dense rows)
     mean = pt.empty((a.size(0),), dtype=pt.float32, device=a.device)
     with pt.cuda.device(a.device):
         _lib.check(lib.s3_svd_row_means(_lib.ptr(a), a.size(0), a.size(1), _lib.ptr(mean), _lib.stream_ptr()))
@@ -63,6 +64,7 @@ def row_means(a: pt.Tensor) -> pt.Tensor:
 def gram(a: pt.Tensor, mean: pt.Tensor, vol: pt.Tensor, vol_div: int = 1, method: str = "tc3") -> pt.Tensor:
     """G[i, j] = sum_m vol[m // vol_div] (a[m, i] - mean[m]) (a[m, j] - mean[m]), fp64 [T, T]."""
     lib = _lib.load()
+    a = a.contiguous()
     t = a.size(1)
     g = pt.empty((t, t), dtype=pt.float64, device=a.device)
     with pt.cuda.device(a.device):
@@ -75,6 +77,7 @@ def project(a: pt.Tensor, mean: pt.Tensor, vs: pt.Tensor) -> pt.Tensor:
     """U = (a - mean[:, None]) @ vs, fp32 [M, r]."""
     lib = _lib.load()
     vs = vs.to(pt.float32).contiguous()
+    a = a.contiguous()
     u = pt.empty((a.size(0), vs.size(1)), dtype=pt.float32, device=a.device)
     with pt.cuda.device(a.device):
         _lib.check(lib.s3_svd_project(_lib.ptr(a), _lib.ptr(mean), _lib.ptr(vs), a.size(0), a.size(1), vs.size(1),
@@ -88,6 +91,7 @@ def project_tc(a: pt.Tensor, mean: pt.Tensor, vol: pt.Tensor, vol_div: int, vs: 
     and un-weighted in the epilogue. fp32 [M, r]."""
     lib = _lib.load()
     vs = vs.to(pt.float32).contiguous()
+    a = a.contiguous()
     u = pt.empty((a.size(0), vs.size(1)), dtype=pt.float32, device=a.device)
     with pt.cuda.device(a.device):
         _lib.check(lib.s3_svd_project_tc(_lib.ptr(a), _lib.ptr(mean), _lib.ptr(vol), vol_div, _lib.ptr(vs), a.size(0),
@@ -174,6 +178,12 @@ def top_eigenpairs(g: pt.Tensor, r: int, tol: float = 1e-7, max_iter: int = 40):
         if excess <= 1.0:
             return w[:r], x[:, :r]
         history.append(excess)
+        if sweep == 0:
+            # residuals contract by about lambda_(b+1) / lambda_i per sweep: without a gap between the r-th Ritz value and
+            # the end of the block (a flat noise tail inside the requested pairs) 40 sweeps cannot deliver 1e-7 --
+            # decided here, after one sweep, instead of iterating first
+            if float(w[r - 1]) < 1.5 * float(w[-1].clamp_min(0.0)) or float(w[r - 1]) <= 0.0:
+                return None
         if sweep >= 6:
             rate = (history[-1] / history[-4]) ** (1.0 / 3.0)          # contraction per sweep, last three sweeps
             if not np.isfinite(rate) or rate >= 0.98 or np.log(excess) / -np.log(rate) > (max_iter - 1 - sweep):
