@@ -184,9 +184,10 @@ interp_warpcell_kernel(const Tin* __restrict__ data, const int32_t* __restrict__
     }
 }
 
-// Dense fp32 batches (row pitch = row length on both sides), the reference's own layout: the round-1 formulation of
-// the same loop, kept because ptxas schedules it best for k = 8 (four predicated row loads in flight at 32 registers
-// = 64 resident warps per SM; C2: 0.391 ms per step against 0.405-0.48 for the strided instantiations on this layout).
+// Dense fp32 batches (row pitch = row length on both sides) whose rows are 16- but not 32-byte aligned, so that the
+// 256-bit path does not apply: the round-1 formulation of the same loop, kept because ptxas schedules it best among the
+// 128-bit variants for k = 8 (four predicated row loads in flight at 32 registers = 64 resident warps per SM; C2: 0.391
+// ms per step against 0.405-0.48 for the strided 128-bit instantiations, 0.375 for the 256-bit kernel on this layout).
 __global__ void __launch_bounds__(512)
 interp_dense_kernel(const float* __restrict__ data, int64_t row_len, const int32_t* __restrict__ idx,
                     const float* __restrict__ w, int64_t n_cells, int k, const int32_t* __restrict__ out_row,
@@ -254,7 +255,7 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
     // Long rows keep one load in flight per warp (more only thrashes the L1, profiles/r2_interp_lab.md).
     const int kunroll = g_kunroll != 0 ? g_kunroll : (g.n_cols <= 256 ? 8 : 1);
     if constexpr (std::is_same<Tin, float>::value && std::is_same<Tout, float>::value && MODE == 0) {
-        if (g_dense && vec_ok && k <= 16 && n_comp == 1 && g.n_cols % 4 == 0 && g.row_stride == g.n_cols &&
+        if (g_dense && !wide && vec_ok && k <= 16 && n_comp == 1 && g.n_cols % 4 == 0 && g.row_stride == g.n_cols &&
             g.out_row_stride == g.n_cols && g_chunk_cols == 0) {
             interp_dense_kernel<<<(unsigned)blocks, warps * 32, 0, stream>>>(
                 reinterpret_cast<const float*>(data), g.n_cols, idx, reinterpret_cast<const float*>(w), n_cells, k,

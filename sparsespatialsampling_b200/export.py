@@ -85,25 +85,34 @@ class KnnTables:
             self._rows_expanded[comps] = (rows[:, None] * comps + ar[None, :]).reshape(-1).contiguous()
         return self._rows_expanded[comps]
 
-    def _stream_state(self, dev, n_src: int, comps: int, chunk: int):
+    def _stream_state(self, dev, n_src: int, comps: int, chunk: int, dense: bool = False):
         """Copy streams (shared) and, per batch geometry, the two input / output device buffers of the host pipeline."""
         if getattr(self, "_copy_streams", None) is None:
             with pt.cuda.device(dev):
                 self._copy_streams = (pt.cuda.Stream(dev), pt.cuda.Stream(dev))
             self._stream_buffers = {}
-        key = (n_src, comps, chunk)
+        key = (n_src, comps, chunk, dense)
         st = self._stream_buffers.get(key)
         if st is None:
             if len(self._stream_buffers) >= 4:              # geometry changed for good: drop the old staging buffers
                 pt.cuda.synchronize(dev)
                 self._stream_buffers.clear()
             with pt.cuda.device(dev):
-                pitch = pitched_columns(chunk)              # 128-byte aligned rows whatever the window length
+                # 128-byte aligned rows whatever the window length; `dense`: the window is the whole (short) batch and
+                # keeps the host layout, so that both transfers are ONE linear copy each instead of a row-wise 2-D copy
+                pitch = chunk if dense else pitched_columns(chunk)
                 st = {"inp": [pt.empty((n_src, comps, pitch), dtype=pt.float32, device=dev) for _ in range(2)],
                       "out": [pt.empty((self.n, comps, pitch), dtype=pt.float32, device=dev) for _ in range(2)],
                       "done": None, "pitch": pitch}
             self._stream_buffers[key] = st
         return st
+
+    # Batches of <= 256 snapshots (the windows of a sharded export) go through the device as ONE dense window: one
+    # linear DMA copy per direction instead of row-wise 2-D copies of 128-256-byte rows, the kernel reads the host
+    # layout; successive batches / fields still overlap each other. Measured on an 8-GPU box (C2 split 4 / 8 ways,
+    # profiles/r2_e2e_short_dense_ab.log): 21.6 -> 18.3 ms and 20.5 -> 13.3 ms per step, i.e. the duplex DMA ceiling of
+    # the box (profiles/r2_pcie_aggregate.log). S3B200_SHORT_DENSE=0 restores the windowed path (A/B).
+    short_batch_dense = os.environ.get("S3B200_SHORT_DENSE", "1") == "1"
 
     @staticmethod
     def default_window(n_src: int, comps: int, t: int) -> int:
@@ -140,6 +149,9 @@ class KnnTables:
             out = pt.empty((self.n, comps, t), dtype=pt.float32, pin_memory=True)
         assert out.is_pinned() and out.is_contiguous() and tuple(out.shape) == (self.n, comps, t)
         chunk = min(int(chunk_snapshots), t) if chunk_snapshots else self.default_window(n_src, comps, t)
+        dense = False
+        if not chunk_snapshots and self.short_batch_dense and t <= 256:
+            chunk, dense = t, True
         if gather is None:
             gather = self._compact()[0].numel() < 0.6 * n_src
         if gather:
@@ -148,7 +160,7 @@ class KnnTables:
             n_stage = int(rows_unique.numel())                  # compact staging buffer: referenced rows only
         else:
             n_stage = n_src
-        st = self._stream_state(dev, n_stage, comps, chunk)
+        st = self._stream_state(dev, n_stage, comps, chunk, dense)
         pitch = st["pitch"]
         h2d, d2h = self._copy_streams
         compute = pt.cuda.current_stream(dev)
