@@ -6,8 +6,10 @@ Strong scaling of the sharded export on the C4 workload (BASELINE.json config 4:
   python -m torch.distributed.run --nproc-per-node N ... scripts/scale_c4.py    (rank r holds T/N snapshots)
 
 Rank 0 generates the grid (n_cells_max = 500 000) and the KNN tables, both are broadcast once (NCCL); every rank
-generates ITS window of the closed-form field on the device in the pitched layout and interpolates it. Timing as in
-bench.py: barrier + synchronize on both sides, CUDA events, max over ranks. One JSON line from rank 0.
+generates ITS window of the closed-form field on the device in the pitched layout and exports it through the public
+entry point `ExportData(distributed=True).export(coordinates, window, "p", n_snapshots_total=T)` (device tensors in,
+device result out, no files). Timing as in bench.py: barrier + synchronize on both sides, CUDA events, max over ranks.
+One JSON line from rank 0.
 """
 import argparse
 import json
@@ -25,7 +27,7 @@ import torch.distributed as dist
 
 import synth
 import sparsespatialsampling_b200 as s3
-from sparsespatialsampling_b200.export import KnnTables
+from sparsespatialsampling_b200.export import ExportData, KnnTables
 from sparsespatialsampling_b200.interpolate import alloc_snapshots
 from sparsespatialsampling_b200.knn import KnnIndex
 from sparsespatialsampling_b200.parallel import broadcast_grid, snapshot_window
@@ -93,15 +95,26 @@ def main():
     for c0 in range(0, ts, 16):                       # closed-form field of THIS window, generated on the device
         c1 = min(c0 + 16, ts)
         data[:, :, c0:c1] = synth.wake_field(xd, t0 + c0, t0 + c1, T, 1, wake["xc"], wake["yc"])
-    out = alloc_snapshots(nc, 1, ts, device=dev)
+    class _Grid:
+        pass
+    g = _Grid()
+    g.n_dimensions, g.faces, g.vertices, g.levels = 3, None, None, None
+    g.centers, g.metric, g.size_initial_cell = centers, pt.zeros(xd.size(0)), 1.0
+    g.save_path, g.save_name, g.grid_name = "/tmp/s3b200_c4", f"c4_rank{rank}", "grid"
+    exp = ExportData(g, write_times=[str(i) for i in range(T)], write_files=False, device=dev, distributed=world > 1)
+    exp._tables_centers, exp._initialized_weights, exp._interpolated_metric = tables, True, True   # built / shared above
+
+    def step():
+        exp.export(x, data, "p", n_snapshots_total=T)
+        return exp._last_fields.centers
     for _ in range(max(args.warmup, 3)):
-        tables.interpolate(data, pt.float32, out=out)
+        out = step()
     barrier()
     e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        tables.interpolate(data, pt.float32, out=out)
+        out = step()
     e1.record()
     barrier()
     ms = rank_max(e0.elapsed_time(e1)) / args.steps

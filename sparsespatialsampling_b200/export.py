@@ -485,7 +485,7 @@ class ExportData:
         if data.dtype not in (pt.float32, pt.float64):
             data = data.to(pt.float32)
         if data.is_cuda:
-            return data.to(self._device).contiguous()
+            return data.to(self._device)         # any row pitch: the kernel takes the strides (no re-packing copy)
         data = data.contiguous()
         if not data.is_pinned():
             try:
