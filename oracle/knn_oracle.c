@@ -145,8 +145,30 @@ static double o_pt_tri_dist2(const double* p, const double* a, const double* b, 
 
 /* geometry_STL_3d.py:81-103 (pyvista select_enclosed_points, check_surface=False) -- VTK is not available
  * offline; documented restatement: within tol of the surface => inside, else parity of +x ray crossings
- * (ray nudged in y/z). par = lo[3], hi[3], tol, triangles[n][9]. PARITY UNPINNED beyond the reference's
- * own tests (tests/test_geometry_STL.py on tests/cube.stl). */
+ * (ray nudged in y/z; a ray that still runs exactly through an edge or vertex of the projected mesh is resolved
+ * by the top-left rule below, i.e. as if nudged further by (eps, eps^2)). par = lo[3], hi[3], tol, triangles[n][9].
+ * PARITY UNPINNED beyond the reference's own tests (tests/test_geometry_STL.py on tests/cube.stl) and the
+ * closed-form solids of tests/test_geometry_surfaces_*.py. This file is compiled with -ffp-contract=off: the sign
+ * of an edge function has to be the exact negative for the neighbouring triangle. */
+static int o_edge_side(double uy, double uz, double vy, double vz) {
+    const double m0 = uy * vz, m1 = uz * vy;
+    const double f = m0 - m1;
+    if (f > 0) return 1;
+    if (f < 0) return -1;
+    if (uz != vz) return uz > vz ? 1 : -1;
+    if (uy != vy) return vy > uy ? 1 : -1;
+    return 0;
+}
+static int o_ray_crosses(double px, double py, double pz, const double* a, const double* b, const double* c) {
+    const double ay = a[1] - py, az = a[2] - pz, by = b[1] - py, bz = b[2] - pz, cy = c[1] - py, cz = c[2] - pz;
+    const int e0 = o_edge_side(ay, az, by, bz), e1 = o_edge_side(by, bz, cy, cz), e2 = o_edge_side(cy, cz, ay, az);
+    if (!((e0 > 0 && e1 > 0 && e2 > 0) || (e0 < 0 && e1 < 0 && e2 < 0))) return 0;
+    const double s0 = ay * bz - az * by, s1 = by * cz - bz * cy, s2 = cy * az - cz * ay;
+    const double sum = (s0 + s1) + s2;
+    if (sum == 0.0) return 0;
+    const double num = (s1 * a[0] + s2 * b[0]) + s0 * c[0];
+    return num / sum > px;
+}
 static int o_stl(const double* p, const double* par, int n_tri) {
     const double *lo = par, *hi = par + 3, tol = par[6], *tri = par + 7;
     for (int a = 0; a < 3; ++a)
@@ -157,13 +179,7 @@ static int o_stl(const double* p, const double* par, int n_tri) {
     for (int t = 0; t < n_tri; ++t) {
         const double *a = tri + 9 * t, *b = a + 3, *c = a + 6;
         if (o_pt_tri_dist2(p, a, b, c) <= tol * tol) near = 1;
-        const double ay = a[1] - py, az = a[2] - pz, by = b[1] - py, bz = b[2] - pz, cy = c[1] - py, cz = c[2] - pz;
-        const double s0 = ay * bz - az * by, s1 = by * cz - bz * cy, s2 = cy * az - cz * ay;
-        if ((s0 > 0 && s1 > 0 && s2 > 0) || (s0 < 0 && s1 < 0 && s2 < 0)) {
-            const double sum = s0 + s1 + s2;
-            const double xh = (s1 * a[0] + s2 * b[0] + s0 * c[0]) / sum;
-            if (xh > p[0]) ++crossings;
-        }
+        crossings += o_ray_crosses(p[0], py, pz, a, b, c);
     }
     return near || (crossings & 1);
 }

@@ -26,15 +26,18 @@ _clib = None
 def _load_c():
     global _clib
     if _clib is None:
-        if not os.path.exists(_SO):
-            try:
-                from . import build as _b
-            except ImportError:  # imported as a top-level module
-                import importlib.util
-                spec = importlib.util.spec_from_file_location("s3_oracle_build", os.path.join(_HERE, "build.py"))
-                _b = importlib.util.module_from_spec(spec)
-                spec.loader.exec_module(_b)
-            _b.build()
+        try:
+            from . import build as _b
+        except ImportError:  # imported as a top-level module
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("s3_oracle_build", os.path.join(_HERE, "build.py"))
+            _b = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(_b)
+        try:
+            _b.build()                      # no-op unless knn_oracle.c is newer than the library
+        except Exception:
+            if not os.path.exists(_SO):
+                raise
         lib = ctypes.CDLL(_SO)
         lib.s3o_knn.restype = None
         lib.s3o_knn.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,

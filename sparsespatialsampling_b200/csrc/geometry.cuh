@@ -134,7 +134,9 @@ __device__ __forceinline__ bool in_pyramid(const double* p, const double* par) {
 // check_surface=False).  VTK is not available offline, so this is the documented restatement:
 // a point is inside if it lies within `tol` (absolute, = tolerance * bbox diagonal as in
 // vtkSelectEnclosedPoints) of the surface, else by the parity of +x ray crossings; the ray is cast
-// through y/z perturbed by irrational offsets of relative size 1e-9 so edges/vertices are not hit.
+// through y/z perturbed by irrational offsets of relative size 1e-9 so edges/vertices are rarely hit, and
+// a ray that still passes exactly through an edge or a vertex of the projected mesh is counted once per
+// surface crossing by the half-open rule of stl_edge_side (below).
 // par = lo[3], hi[3], tol, then n_tri * 9 doubles.
 __device__ __forceinline__ double pt_tri_dist2(const double* p, const double* a, const double* b, const double* c) {
     // closest point on triangle (Ericson, Real-Time Collision Detection 5.1.5)
@@ -185,6 +187,37 @@ __device__ __forceinline__ double pt_tri_dist2(const double* p, const double* a,
     return dx * dx + dy * dy + dz * dz;
 }
 
+// Side of the projected ray point (the origin; u, v are edge end points relative to it, in the y-z plane) with
+// respect to the directed edge u -> v: the sign of cross(u, v), evaluated WITHOUT fused multiply-add so that the two
+// triangles sharing an edge (which see it as u -> v and v -> u) get exactly opposite values. A zero is resolved as if
+// the point were shifted by (eps, eps^2) in (y, z): d cross / dy = u.z - v.z, d cross / dz = v.y - u.y. This is the
+// usual top-left fill rule; it is antisymmetric in (u, v) like the value itself, hence independent of the winding of
+// the triangles, and a ray through a shared edge or vertex of a closed surface is claimed by exactly one triangle
+// per crossing (edge-on triangles, whose three sides cannot agree, by none).
+__device__ __forceinline__ int stl_edge_side(double uy, double uz, double vy, double vz) {
+    const double f = __dsub_rn(__dmul_rn(uy, vz), __dmul_rn(uz, vy));
+    if (f > 0) return 1;
+    if (f < 0) return -1;
+    if (uz != vz) return uz > vz ? 1 : -1;
+    if (uy != vy) return vy > uy ? 1 : -1;
+    return 0;
+}
+
+// +x ray from (px, py, pz) against triangle (a, b, c): point-in-triangle in the y-z plane, then the x of the hit
+__device__ __forceinline__ bool stl_ray_crosses(double px, double py, double pz, const double* a, const double* b,
+                                                const double* c) {
+    const double ay = a[1] - py, az = a[2] - pz, by = b[1] - py, bz = b[2] - pz, cy = c[1] - py, cz = c[2] - pz;
+    const int e0 = stl_edge_side(ay, az, by, bz), e1 = stl_edge_side(by, bz, cy, cz), e2 = stl_edge_side(cy, cz, ay, az);
+    if (!((e0 > 0 && e1 > 0 && e2 > 0) || (e0 < 0 && e1 < 0 && e2 < 0))) return false;
+    const double s0 = __dsub_rn(__dmul_rn(ay, bz), __dmul_rn(az, by));
+    const double s1 = __dsub_rn(__dmul_rn(by, cz), __dmul_rn(bz, cy));
+    const double s2 = __dsub_rn(__dmul_rn(cy, az), __dmul_rn(cz, ay));
+    const double sum = __dadd_rn(__dadd_rn(s0, s1), s2);
+    if (sum == 0.0) return false;
+    const double num = __dadd_rn(__dadd_rn(__dmul_rn(s1, a[0]), __dmul_rn(s2, b[0])), __dmul_rn(s0, c[0]));
+    return num / sum > px;
+}
+
 __device__ __forceinline__ bool in_stl(const double* p, const double* par, int n_tri) {
     const double* lo = par;
     const double* hi = par + 3;
@@ -202,15 +235,7 @@ __device__ __forceinline__ bool in_stl(const double* p, const double* par, int n
         const double* b = a + 3;
         const double* c = a + 6;
         if (pt_tri_dist2(p, a, b, c) <= tol * tol) near = true;
-        // +x ray from (p.x, py, pz): 2-D point-in-triangle in the y-z plane, then x of the hit
-        const double ay = a[1] - py, az = a[2] - pz, by = b[1] - py, bz = b[2] - pz, cy = c[1] - py, cz = c[2] - pz;
-        const double s0 = ay * bz - az * by, s1 = by * cz - bz * cy, s2 = cy * az - cz * ay;
-        const bool allpos = s0 > 0 && s1 > 0 && s2 > 0, allneg = s0 < 0 && s1 < 0 && s2 < 0;
-        if (allpos || allneg) {
-            const double sum = s0 + s1 + s2;
-            const double xh = (s1 * a[0] + s2 * b[0] + s0 * c[0]) / sum;
-            if (xh > p[0]) ++crossings;
-        }
+        if (stl_ray_crosses(p[0], py, pz, a, b, c)) ++crossings;
     }
     return near || (crossings & 1);
 }

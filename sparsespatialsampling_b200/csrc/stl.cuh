@@ -175,17 +175,7 @@ stl_inside_kernel(const StlPoints src, int64_t n_pts, const double* __restrict__
                     const double* b = a + 3;
                     const double* c = a + 6;
                     if (band && !near && pt_tri_dist2(p, a, b, c) <= tol * tol) near = true;
-                    if (in_yz && tb[3] > p[0]) {
-                        const double ay = a[1] - py, az = a[2] - pz, by = b[1] - py, bz = b[2] - pz, cy = c[1] - py,
-                                     cz = c[2] - pz;
-                        const double s0 = ay * bz - az * by, s1 = by * cz - bz * cy, s2 = cy * az - cz * ay;
-                        const bool allpos = s0 > 0 && s1 > 0 && s2 > 0, allneg = s0 < 0 && s1 < 0 && s2 < 0;
-                        if (allpos || allneg) {
-                            const double sum = s0 + s1 + s2;
-                            const double xh = (s1 * a[0] + s2 * b[0] + s0 * c[0]) / sum;
-                            if (xh > p[0]) ++crossings;
-                        }
-                    }
+                    if (in_yz && tb[3] > p[0] && stl_ray_crosses(p[0], py, pz, a, b, c)) ++crossings;
                 }
             }
             __syncthreads();                             // stage (i & 1) and s_tbox may be overwritten now

@@ -105,3 +105,74 @@ def in_l_extrusion(p, height=0.5, margin=0.0):
     inside = box(0, 2, 0, 1, margin) | box(0, 1, 0, 2, margin)
     grown = box(0, 2, 0, 1, -margin) | box(0, 1, 0, 2, -margin)
     return np.where(inside, 1, np.where(~grown, -1, 0))
+
+
+def grid_box_triangles(lo, hi, n=4, flip_every=0):
+    """Axis-aligned box whose faces are n x n quads split along one diagonal: many mesh vertices and edges on lattice
+    planes. `flip_every` > 0 reverses the winding of every flip_every-th triangle (STL files in the wild are not
+    always consistently oriented; the inside test must not care)."""
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    tris = []
+    for axis in range(3):
+        u, v = (axis + 1) % 3, (axis + 2) % 3
+        for side, x in enumerate((lo[axis], hi[axis])):
+            for i in range(n):
+                for j in range(n):
+                    def corner(a, b):
+                        p = np.empty(3)
+                        p[axis] = x
+                        p[u] = lo[u] + (hi[u] - lo[u]) * a / n
+                        p[v] = lo[v] + (hi[v] - lo[v]) * b / n
+                        return p
+                    q = [corner(i, j), corner(i + 1, j), corner(i + 1, j + 1), corner(i, j + 1)]
+                    if side == 0:
+                        q = q[::-1]
+                    tris.append([q[0], q[1], q[2]])
+                    tris.append([q[0], q[2], q[3]])
+    tris = np.array(tris)
+    if flip_every:
+        tris[::flip_every] = tris[::flip_every, ::-1].copy()
+    return tris
+
+
+def ray_through_lattice_points(ext, ys, zs, xs):
+    """Points whose +x ray, AFTER the inside test's own y/z nudge (ext * sqrt(2) * 1e-9, ext * sqrt(3) * 1e-9), passes
+    exactly through the lattice values ys x zs: undo the nudge in floating point, one ulp at a time."""
+    def undo(target, jit):
+        p = np.float64(target) - jit
+        for _ in range(8):
+            s = p + jit
+            if s == target:
+                return p
+            p = np.nextafter(p, np.inf if s < target else -np.inf)
+        raise AssertionError("no pre-image")
+    jy, jz = np.float64(ext) * 1.4142135623730951e-9, np.float64(ext) * 1.7320508075688772e-9
+    return np.array([[x, undo(y, jy), undo(z, jz)] for x in xs for y in ys for z in zs], dtype=np.float64)
+
+
+def two_box_exact_hit_case(flip_every=0):
+    """Two lattice boxes [0,1]^3 and [2,3]x[0,1]^2 in ONE surface, plus points whose nudged +x ray runs exactly through
+    mesh vertices, axis-aligned edges and face diagonals. Returns (triangles, points, inside_expected); a ray from the
+    first box crosses three faces, from the gap two, from the second box one."""
+    tri = np.concatenate([grid_box_triangles((0, 0, 0), (1, 1, 1), 4, flip_every),
+                          grid_box_triangles((2, 0, 0), (3, 1, 1), 4, flip_every)])
+    ext = 3.0
+    lat, gen, xs = [0.25, 0.5, 0.75], [0.1, 0.3721, 0.61], [0.5, 1.5, 2.5]
+    sets = [ray_through_lattice_points(ext, lat, lat, xs),          # through vertices
+            ray_through_lattice_points(ext, lat, gen, xs),          # through edges of constant y
+            ray_through_lattice_points(ext, gen, lat, xs)]          # through edges of constant z
+    diag = ray_through_lattice_points(ext, gen, gen, xs)            # through the quad diagonals: nudged y == nudged z
+    jy, jz = np.float64(ext) * 1.4142135623730951e-9, np.float64(ext) * 1.7320508075688772e-9
+    for r in diag:
+        target = r[1] + jy
+        z = target - jz
+        for _ in range(8):
+            s = z + jz
+            if s == target:
+                break
+            z = np.nextafter(z, np.inf if s < target else -np.inf)
+        assert z + jz == target
+        r[2] = z
+    sets.append(diag)
+    pts = np.concatenate(sets)
+    return tri, pts, (pts[:, 0] == 0.5) | (pts[:, 0] == 2.5)

@@ -229,3 +229,28 @@ def test_stl_tiled_kernel_equals_per_thread_path(cuda, tmp_path, n_sub, n_cells)
     assert pt.equal(flags[0], flags[1])
     vol = float(flags[0].float().mean())
     assert abs(vol - 4.0 / 3.0 * np.pi * 0.31 ** 3) < 0.01                   # Monte-Carlo volume of the sphere
+
+
+@pytest.mark.parametrize("flip_every", [0, 3])
+def test_stl_rays_through_edges_and_vertices(cuda, tmp_path, flip_every):
+    """Rays that hit shared edges, face diagonals and mesh vertices EXACTLY (after the test's own nudge): device (tiled
+    kernel and per-thread path) == oracle == closed form, independent of the triangle winding."""
+    from sparsespatialsampling_b200 import _lib
+    from sparsespatialsampling_b200.geometry import GeometrySTL3D
+    from sparsespatialsampling_b200.geometry.device import GeometryTable, nodes_inside
+    from tests.stl_util import two_box_exact_hit_case
+    tri, pts, want = two_box_exact_hit_case(flip_every)
+    p = tmp_path / "two.stl"
+    write_binary_stl(p, tri)
+    g = GeometrySTL3D("two", False, str(p))
+    got = nodes_inside(g, pt.from_numpy(pts)).numpy()
+    assert np.array_equal(got, want) and np.array_equal(got, orc.points_inside(g, pts))
+    dev = pt.device("cuda")
+    tab = GeometryTable([g], dev)
+    lib = _lib.load()
+    d_pts = pt.from_numpy(pts).to(dev)
+    for stl_geoms, meta in ((tab.stl_geoms, tab.stl_meta), (0, None)):
+        ins = pt.empty(d_pts.size(0), dtype=pt.uint8, device=dev)
+        _lib.check(lib.s3_points_inside(_lib.ptr(d_pts), d_pts.size(0), 3, _lib.ptr(tab.hdr), _lib.ptr(tab.par), 0,
+                                        _lib.ptr(ins), stl_geoms, meta, _lib.stream_ptr()))
+        assert np.array_equal(ins.cpu().numpy().astype(bool), want)

@@ -127,3 +127,16 @@ def test_top_eigenpairs_subspace_iteration_and_fallback():
     flat = pt.cat([pt.logspace(0, -3, 10, dtype=pt.float64), 1e-4 * pt.logspace(0, -2, t - 10, dtype=pt.float64)])
     assert top_eigenpairs((u * flat) @ u.T, 30) is None                   # slowly decaying tail: not worth iterating
     assert top_eigenpairs(g, 200) is None                                 # r not small against T
+
+
+@pytest.mark.parametrize("flip_every", [0, 3])
+def test_stl_oracle_rays_through_edges_and_vertices(tmp_path, flip_every):
+    """The restated STL inside test counts a ray that runs exactly through a shared edge / a vertex of the mesh once
+    per surface crossing (half-open edge rule), whatever the winding of the triangles."""
+    import sparsespatialsampling_b200.geometry as g
+    from tests.stl_util import write_binary_stl, two_box_exact_hit_case
+    tri, pts, want = two_box_exact_hit_case(flip_every)
+    p = tmp_path / "two.stl"
+    write_binary_stl(p, tri)
+    stl = g.GeometrySTL3D("two", False, str(p))
+    assert np.array_equal(orc.points_inside(stl, pts), want)
