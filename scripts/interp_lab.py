@@ -20,7 +20,7 @@ from sparsespatialsampling_b200.export import KnnTables
 from sparsespatialsampling_b200.interpolate import alloc_snapshots
 from sparsespatialsampling_b200.knn import KnnIndex
 
-DEFAULTS = {1: 8, 2: 0, 3: -1, 4: 0, 5: -1, 6: -1, 7: 0, 9: 1}
+DEFAULTS = {1: 8, 2: 0, 3: -1, 4: 0, 5: -1, 6: -1, 7: 0, 8: -1, 9: 1, 12: 0, 13: 0}
 VARIANTS = ["", "9=0", "9=0,6=0", "9=0,6=0,2=1", "6=-1,3=0", "2=2", "1=4", "1=16", "4=512", "7=4"]
 OLD_VARIANTS = ["", "7=2", "7=4", "2=2", "2=2,7=2", "6=1,3=1", "6=1,3=1,7=2", "8=2", "8=2,7=2", "8=2,7=4", "8=2,4=512",
             "8=2,7=2,4=512", "8=4", "8=4,7=2", "8=4,4=512", "8=4,4=256", "8=4,1=4", "8=4,1=4,4=512", "8=2,1=4",
@@ -58,13 +58,23 @@ def main():
     tables = KnnTables(KnnIndex(xd), centers, k)
     nc = tables.n
     n_unique = int(pt.unique(tables.idx_sorted).numel())
-    fields = {}
-    for comps in (1, 2):
-        f = synth.wake_field(xd, 0, T, T, comps)
-        fp = alloc_snapshots(xd.size(0), comps, T, device=dev, zero=True)
-        fp.copy_(f)
-        fields[comps] = {"dense": (f, pt.empty((nc, comps, T), device=dev)),
-                         "pitched": (fp, alloc_snapshots(nc, comps, T, device=dev))}
+    # rotating buffer sets: at least 500 MB touched between two uses of a byte (126 MB L2), as in bench.py
+    per_set = sum((xd.size(0) + nc) * c * T * 4 for c in (1, 2))
+    n_sets = max(1, -(-500 * 1024 * 1024 // per_set)) if T < 1000 else 1
+    sets = []
+    for s_i in range(n_sets):
+        fields = {}
+        for comps in (1, 2):
+            f = synth.wake_field(xd, 0, T, T, comps)
+            fields[comps] = {}
+            if "dense" in args.layouts:
+                fields[comps]["dense"] = (f, pt.empty((nc, comps, T), device=dev))
+            if "pitched" in args.layouts:
+                fp = alloc_snapshots(xd.size(0), comps, T, device=dev, zero=True)
+                fp.copy_(f)
+                fields[comps]["pitched"] = (fp, alloc_snapshots(nc, comps, T, device=dev))
+        sets.append(fields)
+    fields = sets[0]
     b_algo = sum(bench.algorithmic_bytes(n_unique, nc, k, c, T) for c in (1, 2))
     peak, _ = bench.measured_peak()
     variants = [v for v in args.variants.split(";")] if args.variants else VARIANTS
@@ -76,17 +86,17 @@ def main():
             key, val = kv.split("=")
             _lib.tune(int(key), int(val))
         for layout in args.layouts.split(","):
-            def step():
+            def step(i=0):
                 for comps in (1, 2):
-                    d, o = fields[comps][layout]
+                    d, o = sets[i % n_sets][comps][layout]
                     tables.interpolate(d, pt.float32, out=o)
-            for _ in range(args.warmup):
-                step()
+            for i in range(args.warmup * n_sets):
+                step(i)
             pt.cuda.synchronize()
             e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(args.steps):
-                step()
+            for i in range(args.steps):
+                step(i)
             e1.record()
             pt.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.steps
@@ -94,7 +104,7 @@ def main():
             if not base:
                 base["res"] = res
             same = all(pt.equal(a, b) for a, b in zip(res, base["res"]))
-            print(json.dumps({"variant": var or "default", "layout": layout, "k": k, "T": T, "n_cells": nc,
+            print(json.dumps({"variant": var or "default", "layout": layout, "k": k, "T": T, "n_cells": nc, "buffer_sets": n_sets,
                               "ms_per_step": round(ms, 4), "frac": round(b_algo / (ms * 1e-3) / 1e9 / peak, 4),
                               "bit_identical": same}), flush=True)
 

@@ -34,6 +34,9 @@ static int g_carveout = -1;        // key 5: shared-memory carve-out in percent,
 static int g_wide = -1;            // key 6: 256-bit loads (fp32 in/out, pointers and pitches multiples of 32 B): -1 = whenever possible
 static int g_dense = 1;            // key 9: 1 = dense fp32 batches with k <= 16 take interp_dense_kernel
 static int g_kunroll = 0;          // key 7: neighbour-loop unroll (row loads in flight per lane): 1, 4 or 8; 0 = by row length
+static int g_persistent = -1;      // key 8: part-warp persistent kernel: -1 = short rows (see launch_interp), 0 = never, 1 = whenever possible
+static int g_lanes_per_cell = 0;   // key 13: lanes per cell of that kernel (16 or 32), 0 = by row length
+static int g_persist_ctas = 0;     // key 12: resident CTAs per SM it is compiled for (3: 80 registers, 4: 64), 0 = by row length
 extern int g_tc_seg_kblocks;
 extern int g_tc_flush_segments;
 extern int g_tc_pair;
@@ -227,6 +230,100 @@ interp_dense_kernel(const float* __restrict__ data, int64_t row_len, const int32
     }
 }
 
+// Short rows (the time windows of a sharded export: 125-500 snapshots per rank; k = 8: up to ~750 columns).
+// interp_warpcell_kernel spends a whole warp and a CTA slot on one cell: for a 500-byte row that is one 128-bit load
+// per neighbour behind a dependent table load, ~500 issued instructions per cell, and the SM is issue bound (ncu: 84 %
+// issue-active at 0.34 of the HBM roofline). Here the warps are persistent and split into PART-WARPS of LPC lanes:
+//   * a part-warp walks the cells  first + i * stride  on its own (no CTA barrier anywhere); one 256-bit vector per
+//     lane, so a warp request still covers 1 KB of row segments -- of two cells at a time for rows <= 128 columns;
+//   * lane j fetches neighbour j's (index, weight) of the NEXT cell while the rows of the current one are in flight,
+//     parks them in the part-warp's shared-memory slot, and all lanes read them back with uniform LDS.64;
+//   * the components of a point are looped inside (tables read once per cell, not once per component);
+//   * KU row segments are in flight per lane before their FMAs are issued in neighbour order.
+// The part-warps resident on the GPU at any time cover one compact window of consecutive cells (the warps of a CTA:
+// 8-16 consecutive cells, for L1; all CTAs: a few thousand, for L2). A source vector that straddles the end of a row
+// is loaded whole (pitches are multiples of 32 bytes, so the load stays inside the 32-byte sector of the row's last
+// valid column) and stored column by column. Same products in the same order as interp_warpcell_kernel: same bits.
+// KR = table registers per lane (k <= KR * LPC); CTAS = resident CTAs per SM the register budget is cut for.
+template <int LPC, int KU, int KR, int CTAS>
+__global__ void __launch_bounds__(256, CTAS)
+interp_partwarp_kernel(const float* __restrict__ data, const int32_t* __restrict__ idx, const float* __restrict__ w,
+                       int64_t n_cells, int k, const int32_t* __restrict__ out_row, float* __restrict__ out,
+                       const InterpGeom g, int n_comp) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    struct alignas(8) Pair { int32_t i; float w; };
+    constexpr int SUB = 32 / LPC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int sub = lane / LPC, sl = lane % LPC;
+    Pair* my_pairs = reinterpret_cast<Pair*>(s_raw) + (size_t)(warp * SUB + sub) * (KR * LPC);
+    const int64_t stride = (int64_t)gridDim.x * warps * SUB;
+    const int64_t warp_first = ((int64_t)blockIdx.x * warps + warp) * SUB;      // uniform loop bound of the warp
+    int64_t cell = warp_first + sub;
+
+    Pair nxt[KR];
+    int32_t orow_n = 0;
+    auto fetch = [&](int64_t c) {
+#pragma unroll
+        for (int q = 0; q < KR; ++q) {
+            const int j = sl + q * LPC;
+            nxt[q] = Pair{0, 0.f};
+            if (c < n_cells && j < k) nxt[q] = Pair{idx[c * k + j], w[c * k + j]};
+        }
+        orow_n = c < n_cells ? (out_row ? out_row[c] : (int32_t)c) : 0;
+    };
+    fetch(cell);
+    for (int64_t first = warp_first; first < n_cells; first += stride, cell += stride) {
+#pragma unroll
+        for (int q = 0; q < KR; ++q) my_pairs[sl + q * LPC] = nxt[q];
+        const int64_t orow = orow_n;
+        __syncwarp();
+        fetch(cell + stride);
+        if (cell < n_cells) {
+            for (int comp = 0; comp < n_comp; ++comp) {
+                float* dst = out + orow * g.out_row_stride + (int64_t)comp * g.out_comp_stride;
+                for (int col = sl * 8; col < (int)g.n_cols; col += LPC * 8) {
+                    float acc[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+                    const float* colbase = data + (int64_t)comp * g.comp_stride + col;
+                    int j = 0;
+                    for (; j + KU <= k; j += KU) {
+                        Vec<float, 8> x[KU];
+                        float wj[KU];
+#pragma unroll
+                        for (int u = 0; u < KU; ++u) {
+                            const Pair p = my_pairs[j + u];
+                            wj[u] = p.w;
+                            x[u] = ld_vec<float, 8>(colbase + (int64_t)p.i * g.row_stride);
+                        }
+#pragma unroll
+                        for (int u = 0; u < KU; ++u)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[e] = fmaf(wj[u], x[u].v[e], acc[e]);
+                    }
+                    for (; j < k; ++j) {
+                        const Pair p = my_pairs[j];
+                        const Vec<float, 8> x = ld_vec<float, 8>(colbase + (int64_t)p.i * g.row_stride);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p.w, x.v[e], acc[e]);
+                    }
+                    if (col + 8 <= (int)g.n_cols) {
+                        Vec<float, 8> ov;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) ov.v[e] = acc[e];
+                        st_vec<float, 8>(dst + col, ov);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (col + e < (int)g.n_cols) dst[col + e] = acc[e];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <typename Tin, typename Tw, typename Tout, int MODE>
 static int launch_interp(const void* data, const int32_t* idx, const void* w, int64_t n_cells, int k,
                          const int32_t* out_row, void* out, int n_comp, InterpGeom g, cudaStream_t stream) {
@@ -254,6 +351,50 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
     // index -> row load -> FMA, one load latency per neighbour; eight neighbours' loads are issued as a batch there.
     // Long rows keep one load in flight per warp (more only thrashes the L1, profiles/r2_interp_lab.md).
     const int kunroll = g_kunroll != 0 ? g_kunroll : (g.n_cols <= 256 ? 8 : 1);
+    if constexpr (std::is_same<Tin, float>::value && std::is_same<Tout, float>::value && MODE == 0) {
+        // measured cross-over against the warp-per-cell kernel (profiles/r2_interp_lab.md, run 8): k = 8 wins up to 750
+        // columns (T = 1000: 0.352 against 0.346 ms), k = 26 up to 500 (T = 1000: 5.8 against 3.6 ms)
+        const bool short_rows = g.n_cols <= (k <= 16 ? 768 : 512);
+        if (wide_ok && k <= 64 && g.n_cols < (1 << 30) && g_chunk_cols == 0 &&
+            (g_persistent == 1 || (g_persistent < 0 && short_rows))) {
+            int lpc = g_lanes_per_cell ? g_lanes_per_cell : (g.n_cols <= 128 ? 16 : 32);
+            if (k > 2 * lpc) lpc = 32;
+            const int kr = k <= lpc ? 1 : 2;
+            const int ku = g_kunroll == 8 ? 8 : 4;
+            // whole-warp rows with few neighbours run best at 4 CTAs (32 warps) per SM, the two-cells-per-warp shape and
+            // k = 26 at 3 (T = 500: 0.181 against 0.191 ms, T = 125: 0.066 against 0.065)
+            const int per_sm_built = g_persist_ctas ? g_persist_ctas : (lpc == 32 && k <= 16 ? 4 : 3);
+            const int sub = 32 / lpc;
+            const int pw = warps > 8 ? 8 : warps;                  // __launch_bounds__(256, ...)
+            const int threads = pw * 32;
+            const size_t sm = (size_t)pw * sub * kr * lpc * 8;
+            const float* d_f = reinterpret_cast<const float*>(data);
+            const float* w_f = reinterpret_cast<const float*>(w);
+            float* o_f = reinterpret_cast<float*>(out);
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+#define S3_PARTWARP(L, K_, R, C)                                                                                   \
+    do {                                                                                                           \
+        auto kern = interp_partwarp_kernel<L, K_, R, C>;                                                           \
+        int per_sm = 1;                                                                                            \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, sm);                                 \
+        if (per_sm < 1) per_sm = 1;                                                                                \
+        const int64_t want = ceil_div(n_cells, (int64_t)pw * sub);                                                 \
+        const int64_t ctas = want < (int64_t)n_sm * per_sm ? want : (int64_t)n_sm * per_sm;                        \
+        kern<<<(unsigned)ctas, threads, sm, stream>>>(d_f, idx, w_f, n_cells, k, out_row, o_f, g, n_comp);         \
+    } while (0)
+#define S3_PARTWARP_C(L, K_, R) do { if (ku == 8) S3_PARTWARP(L, 8, R, 2); else if (per_sm_built == 4) S3_PARTWARP(L, 4, R, 4); else S3_PARTWARP(L, 4, R, 3); } while (0)
+#define S3_PARTWARP_R(L) do { if (kr == 1) S3_PARTWARP_C(L, 0, 1); else S3_PARTWARP_C(L, 0, 2); } while (0)
+            if (lpc == 16) S3_PARTWARP_R(16); else S3_PARTWARP_R(32);
+#undef S3_PARTWARP_R
+#undef S3_PARTWARP_C
+#undef S3_PARTWARP
+            S3_LAUNCH_CHECK();
+            note_launch(1);
+            return S3_OK;
+        }
+    }
     if constexpr (std::is_same<Tin, float>::value && std::is_same<Tout, float>::value && MODE == 0) {
         if (g_dense && !wide && vec_ok && k <= 16 && n_comp == 1 && g.n_cols % 4 == 0 && g.row_stride == g.n_cols &&
             g.out_row_stride == g.n_cols && g_chunk_cols == 0) {
@@ -333,6 +474,9 @@ extern "C" int s3x_tune(int key, int value) {
         case 6: S3_REQUIRE(value >= -1 && value <= 1, "s3x_tune: wide must be -1 (auto), 0 or 1"); g_wide = value; return S3_OK;
         case 9: S3_REQUIRE(value == 0 || value == 1, "s3x_tune: dense kernel must be 0 or 1"); g_dense = value; return S3_OK;
         case 7: S3_REQUIRE(value == 0 || value == 1 || value == 4 || value == 8, "s3x_tune: neighbour-loop unroll must be 0 (auto), 1, 4 or 8"); g_kunroll = value; return S3_OK;
+        case 8: S3_REQUIRE(value >= -1 && value <= 1, "s3x_tune: part-warp kernel must be -1 (short rows), 0 (never) or 1 (whenever possible)"); g_persistent = value; return S3_OK;
+        case 12: S3_REQUIRE(value == 0 || value == 3 || value == 4, "s3x_tune: resident CTAs per SM must be 0 (by row length), 3 or 4"); g_persist_ctas = value; return S3_OK;
+        case 13: S3_REQUIRE(value == 0 || value == 16 || value == 32, "s3x_tune: lanes per cell must be 0 (by row length), 16 or 32"); g_lanes_per_cell = value; return S3_OK;
         case 30: S3_REQUIRE(value == 0 || value == 1, "s3x_tune: curve must be 0 (Morton) or 1 (Hilbert)"); g_curve = value; return S3_OK;
         case 10: S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3x_tune: K-blocks per TMEM segment must be >= 1"); g_tc_seg_kblocks = value; return S3_OK;
         case 11: S3_REQUIRE(value >= 1 && value <= (1 << 20), "s3x_tune: segments per fp64 flush must be >= 1"); g_tc_flush_segments = value; return S3_OK;

@@ -188,6 +188,7 @@ def test_launch_variants_are_bit_identical(cuda, tune):
     from sparsespatialsampling_b200.interpolate import interp_gather, to_pitched
     cases = [_local_case(3000, 900, 8, 1, 1000, 1), _local_case(3000, 300, 26, 2, 333, 2)]
     defaults = {1: 8, 2: 0, 3: -1, 4: 0, 6: -1, 7: 0, 9: 1}
+    _lib.tune(8, 0)                                   # reference results: the warp-per-cell kernel
     want = []
     for data, idx, w in cases:
         want.append(interp_gather(to_pitched(pt.from_numpy(data).cuda()), pt.from_numpy(idx).cuda(),
@@ -206,6 +207,45 @@ def test_launch_variants_are_bit_identical(cuda, tune):
             assert np.array_equal(got64.cpu().numpy(), orc.interpolate(w, idx.astype(np.int64), data))
     finally:
         for key, value in defaults.items():
+            _lib.tune(key, value)
+        _lib.tune(8, PARTWARP_DEFAULT)
+
+
+PARTWARP_DEFAULT = -1
+
+
+@pytest.mark.parametrize("T", [125, 250, 61, 8, 333, 1000])
+@pytest.mark.parametrize("k,D", [(8, 1), (8, 2), (26, 3), (5, 1), (40, 1)])
+def test_partwarp_kernel_is_bit_identical(cuda, T, k, D):
+    """interp_partwarp_kernel (short rows of a sharded export: persistent part-warps, tables of the next cell fetched
+    ahead, whole 256-bit vectors loaded across the row end) against the warp-per-cell kernel: same bits for every
+    lanes-per-cell / load batch / CTA size, nothing written behind the last column of a row."""
+    from sparsespatialsampling_b200 import _lib
+    from sparsespatialsampling_b200.interpolate import interp_gather, to_pitched, alloc_snapshots
+    data, idx, w = _local_case(2500, 1111, k, D, T, 5)
+    d = to_pitched(pt.from_numpy(data).cuda())
+    i_d, w_d = pt.from_numpy(idx).cuda(), pt.from_numpy(w).float().cuda()
+    perm = pt.randperm(1111, generator=pt.Generator().manual_seed(0)).to(pt.int32).cuda()
+    knobs = ((8, PARTWARP_DEFAULT), (12, 0), (13, 0), (7, 0), (1, 8))
+    try:
+        _lib.tune(8, 0)
+        want = interp_gather(d, i_d, w_d)
+        want_perm = interp_gather(d, i_d, w_d, out_row=perm)
+        for tune in ("8=1", "8=1,7=8", "8=1,12=4", "8=1,12=3", "8=1,13=32", "8=1,13=16,7=8", "8=1,1=4", "8=1,1=3,13=16", "8=-1"):
+            for key, value in knobs:
+                _lib.tune(key, value)
+            for kv in tune.split(","):
+                key, value = kv.split("=")
+                _lib.tune(int(key), int(value))
+            out = alloc_snapshots(1111, D, T, device=d.device)
+            out._base.fill_(-7.0)
+            got = interp_gather(d, i_d, w_d, out=out)
+            assert pt.equal(got, want), tune
+            if out._base.size(-1) > T:
+                assert bool((out._base[..., T:] == -7.0).all()), tune          # row padding untouched
+            assert pt.equal(interp_gather(d, i_d, w_d, out_row=perm), want_perm), tune
+    finally:
+        for key, value in knobs:
             _lib.tune(key, value)
 
 
