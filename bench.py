@@ -508,7 +508,7 @@ def run_ours(args):
                     "gram_useful_tflops": gram_flop / (svd_ms["tc3"] * 1e-3) / 1e12,
                     "compute_svd_s": t_svd, "rank": r, "s0": float(s_val[0])}
 
-    # ---- roofline of the dominant kernel (interp_warpcell_kernel; a step is two launches of it), per GPU
+    # ---- roofline of the dominant kernel (the interpolation kernel; a step is two launches of it), per GPU
     def b_algo(out_bytes=4):
         return (algorithmic_bytes(n_unique, n_cells, k, 1, ts, out_bytes) +
                 algorithmic_bytes(n_unique, n_cells, k, 2, ts, out_bytes))
@@ -556,7 +556,9 @@ def run_ours(args):
                    "tune": args.tune or None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                     "kernel": "interp_warpcell_kernel", "per": "GPU (rank 0's window)",
+                     # csrc/interp.cu launch_interp: rows of <= 768 columns (k <= 16) take the part-warp kernel
+                     "kernel": "interp_warpcell_kernel" if ts > 768 else "interp_partwarp_kernel",
+                     "per": "GPU (rank 0's window)",
                      "algorithmic_bytes_per_step": b_algo(), "frac_of_nominal_8TBs": achieved / 8000.0,
                      # what a gather without any cache re-use would move (every reference read from DRAM)
                      "naive_gather_bytes_per_step": naive_bytes,
