@@ -249,7 +249,7 @@ template <int LPC, int KU, int KR, int CTAS>
 __global__ void __launch_bounds__(256, CTAS)
 interp_partwarp_kernel(const float* __restrict__ data, const int32_t* __restrict__ idx, const float* __restrict__ w,
                        int64_t n_cells, int k, const int32_t* __restrict__ out_row, float* __restrict__ out,
-                       const InterpGeom g, int n_comp) {
+                       const InterpGeom g, int n_comp, int store_w) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     struct alignas(8) Pair { int32_t i; float w; };
     constexpr int SUB = 32 / LPC;
@@ -307,11 +307,29 @@ interp_partwarp_kernel(const float* __restrict__ data, const int32_t* __restrict
 #pragma unroll
                         for (int e = 0; e < 8; ++e) acc[e] = fmaf(p.w, x.v[e], acc[e]);
                     }
-                    if (col + 8 <= (int)g.n_cols) {
+                    // result rows need not share the alignment of the source rows (a dense [Nc, D, 250] result has
+                    // 8-byte aligned rows): store_w = widest vector (in floats) every result segment is aligned for
+                    if (col + 8 <= (int)g.n_cols && store_w == 8) {
                         Vec<float, 8> ov;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) ov.v[e] = acc[e];
                         st_vec<float, 8>(dst + col, ov);
+                    } else if (col + 8 <= (int)g.n_cols && store_w == 4) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            Vec<float, 4> ov;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) ov.v[e] = acc[4 * h + e];
+                            st_vec<float, 4>(dst + col + 4 * h, ov);
+                        }
+                    } else if (col + 8 <= (int)g.n_cols && store_w == 2) {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            Vec<float, 2> ov;
+                            ov.v[0] = acc[2 * h];
+                            ov.v[1] = acc[2 * h + 1];
+                            st_vec<float, 2>(dst + col + 2 * h, ov);
+                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 8; ++e)
@@ -353,9 +371,14 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
     const int kunroll = g_kunroll != 0 ? g_kunroll : (g.n_cols <= 256 ? 8 : 1);
     if constexpr (std::is_same<Tin, float>::value && std::is_same<Tout, float>::value && MODE == 0) {
         // measured cross-over against the warp-per-cell kernel (profiles/r2_interp_lab.md, run 8): k = 8 wins up to 750
-        // columns (T = 1000: 0.352 against 0.346 ms), k = 26 up to 500 (T = 1000: 5.8 against 3.6 ms)
-        const bool short_rows = g.n_cols <= (k <= 16 ? 768 : 512);
-        if (wide_ok && k <= 64 && g.n_cols < (1 << 30) && g_chunk_cols == 0 &&
+        // columns (T = 1000: 0.352 against 0.346 ms); k = 26 on the 10 M-point C4 cloud wins at 250 (0.98 against 1.22 ms)
+        // and loses at 500 (2.31 against 1.96 ms)
+        const bool short_rows = g.n_cols <= (k <= 16 ? 768 : 256);
+        // 256-bit loads need 32-byte aligned SOURCE segments only; the stores adapt to the result's alignment
+        const bool src_wide_ok = (uintptr_t)data % 32 == 0 && g.row_stride % 8 == 0 && g.comp_stride % 8 == 0;
+        const uintptr_t out_bits = (uintptr_t)out | (uintptr_t)(g.out_row_stride * 4) | (uintptr_t)(g.out_comp_stride * 4);
+        const int store_w = out_bits % 32 == 0 ? 8 : out_bits % 16 == 0 ? 4 : out_bits % 8 == 0 ? 2 : 1;
+        if (src_wide_ok && k <= 64 && g.n_cols < (1 << 30) && g_chunk_cols == 0 &&
             (g_persistent == 1 || (g_persistent < 0 && short_rows))) {
             int lpc = g_lanes_per_cell ? g_lanes_per_cell : (g.n_cols <= 128 ? 16 : 32);
             if (k > 2 * lpc) lpc = 32;
@@ -382,7 +405,7 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
         if (per_sm < 1) per_sm = 1;                                                                                \
         const int64_t want = ceil_div(n_cells, (int64_t)pw * sub);                                                 \
         const int64_t ctas = want < (int64_t)n_sm * per_sm ? want : (int64_t)n_sm * per_sm;                        \
-        kern<<<(unsigned)ctas, threads, sm, stream>>>(d_f, idx, w_f, n_cells, k, out_row, o_f, g, n_comp);         \
+        kern<<<(unsigned)ctas, threads, sm, stream>>>(d_f, idx, w_f, n_cells, k, out_row, o_f, g, n_comp, store_w); \
     } while (0)
 #define S3_PARTWARP_C(L, K_, R) do { if (ku == 8) S3_PARTWARP(L, 8, R, 2); else if (per_sm_built == 4) S3_PARTWARP(L, 4, R, 4); else S3_PARTWARP(L, 4, R, 3); } while (0)
 #define S3_PARTWARP_R(L) do { if (kr == 1) S3_PARTWARP_C(L, 0, 1); else S3_PARTWARP_C(L, 0, 2); } while (0)

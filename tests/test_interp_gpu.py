@@ -214,7 +214,7 @@ def test_launch_variants_are_bit_identical(cuda, tune):
 PARTWARP_DEFAULT = -1
 
 
-@pytest.mark.parametrize("T", [125, 250, 61, 8, 333, 1000])
+@pytest.mark.parametrize("T", [125, 250, 61, 8, 100, 333, 1000])
 @pytest.mark.parametrize("k,D", [(8, 1), (8, 2), (26, 3), (5, 1), (40, 1)])
 def test_partwarp_kernel_is_bit_identical(cuda, T, k, D):
     """interp_partwarp_kernel (short rows of a sharded export: persistent part-warps, tables of the next cell fetched
@@ -243,7 +243,9 @@ def test_partwarp_kernel_is_bit_identical(cuda, T, k, D):
             assert pt.equal(got, want), tune
             if out._base.size(-1) > T:
                 assert bool((out._base[..., T:] == -7.0).all()), tune          # row padding untouched
+            # dense result (rows aligned to 32 / 16 / 8 / 4 bytes depending on T): 256-bit loads, narrower stores
             assert pt.equal(interp_gather(d, i_d, w_d, out_row=perm), want_perm), tune
+            assert pt.equal(interp_gather(d, i_d, w_d), want), tune
     finally:
         for key, value in knobs:
             _lib.tune(key, value)
