@@ -394,17 +394,25 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
             const float* d_f = reinterpret_cast<const float*>(data);
             const float* w_f = reinterpret_cast<const float*>(w);
             float* o_f = reinterpret_cast<float*>(out);
-            int dev = 0, n_sm = 148;
+            int dev = 0;
             cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            // resident CTAs of the whole device per (device, instantiation, CTA size): queried once, the launch itself
+            // stays free of driver queries (benign race: every thread computes the same number)
+            static int s_resident[16][2][2][3][9];
+            int* slot = (dev >= 0 && dev < 16) ? &s_resident[dev][lpc == 32][kr - 1][ku == 8 ? 0 : per_sm_built - 2][pw] : nullptr;
 #define S3_PARTWARP(L, K_, R, C)                                                                                   \
     do {                                                                                                           \
         auto kern = interp_partwarp_kernel<L, K_, R, C>;                                                           \
-        int per_sm = 1;                                                                                            \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, sm);                                 \
-        if (per_sm < 1) per_sm = 1;                                                                                \
+        int resident = slot ? *slot : 0;                                                                           \
+        if (resident <= 0) {                                                                                       \
+            int per_sm = 1, n_sm = 148;                                                                            \
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);                                    \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, sm);                             \
+            resident = n_sm * (per_sm < 1 ? 1 : per_sm);                                                           \
+            if (slot) *slot = resident;                                                                            \
+        }                                                                                                          \
         const int64_t want = ceil_div(n_cells, (int64_t)pw * sub);                                                 \
-        const int64_t ctas = want < (int64_t)n_sm * per_sm ? want : (int64_t)n_sm * per_sm;                        \
+        const int64_t ctas = want < (int64_t)resident ? want : (int64_t)resident;                                  \
         kern<<<(unsigned)ctas, threads, sm, stream>>>(d_f, idx, w_f, n_cells, k, out_row, o_f, g, n_comp, store_w); \
     } while (0)
 #define S3_PARTWARP_C(L, K_, R) do { if (ku == 8) S3_PARTWARP(L, 8, R, 2); else if (per_sm_built == 4) S3_PARTWARP(L, 4, R, 4); else S3_PARTWARP(L, 4, R, 3); } while (0)
