@@ -169,8 +169,11 @@ int s3_sumsq(const double* d_x, int64_t n, double* d_out, void* stream);
  * ELEMENTS: row_stride between source points, comp_stride between the components of a point; the result
  * [n_cells, n_comp, n_cols] likewise (out_row_stride, out_comp_stride). Dense tensors: comp_stride = n_cols,
  * row_stride = n_comp * n_cols. The kernel is built for row pitches that are multiples of 128 bytes (every warp
- * request then covers whole cache lines); any stride is accepted, 16-byte aligned strides and base
- * pointers take the 128-bit path, everything else a scalar one.
+ * request then covers whole cache lines); any stride is accepted: 32-byte aligned strides and base
+ * pointers take 256-bit loads (fp32 -> fp32), 16-byte aligned ones the 128-bit path, everything else a scalar one.
+ * fp32 rows of up to 768 columns (the time windows of a sharded export) whose SOURCE is 32-byte aligned run in
+ * a kernel of their own; it may load, never store, the (< 32) bytes between the last column of a row and the next
+ * 32-byte boundary -- inside the row pitch by the alignment rule above.
  * dtypes: (data F32, out F32): w is fp32, fp32 FMA accumulation;
  *         (data F32|F64, out F64): w is fp64, products and sequential adds in fp64 (reference order).
  * d_out_row: optional int32 [n_cells] -- row of `out` that receives cell c (cells may be passed in
