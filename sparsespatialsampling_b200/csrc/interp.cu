@@ -32,6 +32,7 @@ static int g_pairs = -1;           // key 3: (idx, w) broadcast: 0 = SHFL, 1 = s
 static int g_chunk_cols = 0;       // key 4: columns per blockIdx.y window, 0 = whole row
 static int g_carveout = -1;        // key 5: shared-memory carve-out in percent, -1 = driver default
 static int g_wide = -1;            // key 6: 256-bit loads (fp32 in/out, pointers and pitches multiples of 32 B): -1 = whenever possible
+static int g_wide64 = 1;           // key 16: 256-bit path of the fp64-result mode
 static int g_dense = 1;            // key 9: 1 = dense fp32 batches with k <= 16 take interp_dense_kernel
 static int g_kunroll = 0;          // key 7: neighbour-loop unroll (row loads in flight per lane): 1, 4 or 8; 0 = by row length
 static int g_persistent = -1;      // key 8: part-warp persistent kernel: -1 = short rows (see launch_interp), 0 = never, 1 = whenever possible
@@ -61,9 +62,24 @@ __device__ __forceinline__ Vec<float, 8> ld_vec<float, 8>(const float* p) {
                  : "l"(p));
     return r;
 }
+template <>
+__device__ __forceinline__ Vec<double, 4> ld_vec<double, 4>(const double* p) {
+    Vec<double, 4> r;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
+}
 template <typename T, int V>
 __device__ __forceinline__ void st_vec(T* p, const Vec<T, V>& x) {
     *reinterpret_cast<Vec<T, V>*>(p) = x;
+}
+template <>
+__device__ __forceinline__ void st_vec<double, 4>(double* p, const Vec<double, 4>& x) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x.v[0]), "d"(x.v[1]), "d"(x.v[2]), "d"(x.v[3]) : "memory");
+}
+template <>
+__device__ __forceinline__ void st_vec<double, 8>(double* p, const Vec<double, 8>& x) {      // two 256-bit stores
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x.v[0]), "d"(x.v[1]), "d"(x.v[2]), "d"(x.v[3]) : "memory");
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "d"(x.v[4]), "d"(x.v[5]), "d"(x.v[6]), "d"(x.v[7]) : "memory");
 }
 template <>
 __device__ __forceinline__ void st_vec<float, 8>(float* p, const Vec<float, 8>& x) {
@@ -363,8 +379,14 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
                          g.comp_stride % 8 == 0 && g.out_row_stride % 8 == 0 && g.out_comp_stride % 8 == 0;
     // short rows (time windows of a sharded export): a 256-column warp step would leave most lanes idle
     const bool wide = wide_ok && (g_wide == 1 || (g_wide < 0 && g.n_cols >= 384));
-    const int unroll = g_unroll != 0 ? g_unroll : (wide ? (k > 16 ? 2 : 1) : (g.n_cols > 128 ? 2 : 1));
-    const bool pairs = g_pairs >= 0 ? g_pairs != 0 : (wide || k > 16);
+    // the reference's result dtype (fp64 sums): 256-bit loads (8 floats / 4 doubles per lane), 256-bit stores
+    constexpr int VW64 = 32 / sizeof(Tin);
+    const bool wide64 = MODE == 1 && std::is_same<Tout, double>::value && g_wide64 && vec_ok &&
+                        (uintptr_t)data % 32 == 0 && (uintptr_t)out % 32 == 0 && g.row_stride % VW64 == 0 &&
+                        g.comp_stride % VW64 == 0 && g.out_row_stride % 4 == 0 && g.out_comp_stride % 4 == 0 &&
+                        (g_wide == 1 || (g_wide < 0 && g.n_cols >= 384));
+    const int unroll = g_unroll != 0 ? g_unroll : ((wide || wide64) ? (k > 16 ? 2 : 1) : (g.n_cols > 128 ? 2 : 1));
+    const bool pairs = g_pairs >= 0 ? g_pairs != 0 : (wide || wide64 || k > 16);
     // Rows of one or two warp steps (the time windows of a sharded export): the warp is bound by the chain
     // index -> row load -> FMA, one load latency per neighbour; eight neighbours' loads are issued as a batch there.
     // Long rows keep one load in flight per warp (more only thrashes the L1, profiles/r2_interp_lab.md).
@@ -437,7 +459,7 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
             return S3_OK;
         }
     }
-    const int v = wide ? 8 : (vec_ok ? VFULL : 1);
+    const int v = wide ? 8 : wide64 ? VW64 : (vec_ok ? VFULL : 1);
     const int64_t step = (int64_t)32 * v * unroll;
     // all rows share their offset inside a 128-byte line when the pitches are multiples of 128 bytes: shorten the
     // first step by that offset so that every later warp request is line aligned
@@ -481,6 +503,14 @@ static int launch_interp(const void* data, const int32_t* idx, const void* w, in
             return S3_OK;
         }
     }
+    if constexpr (MODE == 1 && std::is_same<Tout, double>::value) {
+        if (wide64) {
+            S3_WARPCELL_UP(VW64);
+            S3_LAUNCH_CHECK();
+            note_launch(1);
+            return S3_OK;
+        }
+    }
     if (vec_ok) S3_WARPCELL_UP(VFULL); else S3_WARPCELL_UP(1);
 #undef S3_WARPCELL_UP
 #undef S3_WARPCELL
@@ -503,6 +533,7 @@ extern "C" int s3x_tune(int key, int value) {
         case 4: S3_REQUIRE(value >= 0, "s3x_tune: window columns must be >= 0"); g_chunk_cols = value; return S3_OK;
         case 5: S3_REQUIRE(value >= -1 && value <= 100, "s3x_tune: carve-out must be -1 or 0..100"); g_carveout = value; return S3_OK;
         case 6: S3_REQUIRE(value >= -1 && value <= 1, "s3x_tune: wide must be -1 (auto), 0 or 1"); g_wide = value; return S3_OK;
+        case 16: S3_REQUIRE(value == 0 || value == 1, "s3x_tune: fp64 wide path must be 0 or 1"); g_wide64 = value; return S3_OK;
         case 9: S3_REQUIRE(value == 0 || value == 1, "s3x_tune: dense kernel must be 0 or 1"); g_dense = value; return S3_OK;
         case 7: S3_REQUIRE(value == 0 || value == 1 || value == 4 || value == 8, "s3x_tune: neighbour-loop unroll must be 0 (auto), 1, 4 or 8"); g_kunroll = value; return S3_OK;
         case 8: S3_REQUIRE(value >= -1 && value <= 1, "s3x_tune: part-warp kernel must be -1 (short rows), 0 (never) or 1 (whenever possible)"); g_persistent = value; return S3_OK;

@@ -180,14 +180,15 @@ def test_time_window_views_with_a_common_line_offset(cuda, offset):
 
 
 @pytest.mark.parametrize("tune", ["1=4", "1=16", "2=1", "2=2", "3=0", "3=1", "4=256", "4=128,2=2", "6=1", "6=1,2=2",
-                                  "6=0", "7=4", "7=8", "7=1", "7=4,3=1,2=2", "6=1,7=4", "9=0", "9=0,6=0,2=1"])
+                                  "6=0", "7=4", "7=8", "7=1", "7=4,3=1,2=2", "6=1,7=4", "9=0", "9=0,6=0,2=1", "16=0", "16=1,3=0",
+                                  "16=1,2=2"])
 def test_launch_variants_are_bit_identical(cuda, tune):
     """The launch knobs of the A/B harness (warps per CTA, column vectors per step, shared-memory pairs, column
     windows, 256-bit loads, neighbour-loop batching) change scheduling only: same sums in the same order."""
     from sparsespatialsampling_b200 import _lib
     from sparsespatialsampling_b200.interpolate import interp_gather, to_pitched
     cases = [_local_case(3000, 900, 8, 1, 1000, 1), _local_case(3000, 300, 26, 2, 333, 2)]
-    defaults = {1: 8, 2: 0, 3: -1, 4: 0, 6: -1, 7: 0, 9: 1}
+    defaults = {1: 8, 2: 0, 3: -1, 4: 0, 6: -1, 7: 0, 9: 1, 16: 1}
     _lib.tune(8, 0)                                   # reference results: the warp-per-cell kernel
     want = []
     for data, idx, w in cases:
@@ -202,9 +203,14 @@ def test_launch_variants_are_bit_identical(cuda, tune):
                 got = interp_gather(layout(pt.from_numpy(data).cuda()), pt.from_numpy(idx).cuda(),
                                     pt.from_numpy(w).float().cuda())
                 assert pt.equal(got, ref)
-            got64 = interp_gather(pt.from_numpy(data).cuda(), pt.from_numpy(idx).cuda(), pt.from_numpy(w).cuda(),
-                                  out_dtype=pt.float64)
-            assert np.array_equal(got64.cpu().numpy(), orc.interpolate(w, idx.astype(np.int64), data))
+            want64 = orc.interpolate(w, idx.astype(np.int64), data)
+            for layout in (to_pitched, lambda x: x):           # pitched: the 256-bit path of the fp64-result mode
+                got64 = interp_gather(layout(pt.from_numpy(data).cuda()), pt.from_numpy(idx).cuda(),
+                                      pt.from_numpy(w).cuda(), out_dtype=pt.float64)
+                assert np.array_equal(got64.cpu().numpy(), want64)
+            d64 = to_pitched(pt.from_numpy(data).double().cuda())
+            got64 = interp_gather(d64, pt.from_numpy(idx).cuda(), pt.from_numpy(w).cuda(), out_dtype=pt.float64)
+            assert np.array_equal(got64.cpu().numpy(), orc.interpolate(w, idx.astype(np.int64), data.astype(np.float64)))
     finally:
         for key, value in defaults.items():
             _lib.tune(key, value)
